@@ -1,0 +1,816 @@
+// libparadis_sl.so -- fused semi-Lagrangian advection + GeoCyclic padding for B200 (sm_100a).
+//
+// Replaces the reference's Python hot path model/advection.py:129-169 and
+// model/padding.py:11-39 (see include/paradis_sl.h for the boundary).
+//
+// Kernels
+//   pole_means_kernel      zonal means of rows 0 / H-1 (advection.py:100-114), deterministic
+//   sl_fwd_kernel          backtrack + GeoCyclic index map + bilinear/bicubic gather, fused
+//   pole_rows_fix_kernel   post pole-mean of the output rows 0 / H-1
+//   sl_bwd_arrival_kernel  per arrival point: grad_u, grad_v (+ row class of the departure cell)
+//   plane_reach_kernel     per-plane max |row class| (bounds the inverse-stencil window)
+//   sl_bwd_gather_kernel   grad_field: each output row gathers the arrival points whose stencil
+//                          covers it (inverse stencils), fixed order, no atomics
+//   geocyclic_pad_{fwd,bwd}_kernel  standalone padding op and its adjoint
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/paradis_sl.h"
+#include "sl_device.cuh"
+
+using namespace psl;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PARADIS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return PARADIS_OK;
+}
+
+extern "C" int paradis_sl_abi_version(void) { return PARADIS_SL_ABI_VERSION; }
+extern "C" const char* paradis_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ const float* plane_ptr(const float* base, long long sB, int V, int rows,
+                                                  int W, int pl) {
+  const int b = pl / V, c = pl - b * V;
+  return base + (long long)b * sB + (long long)c * rows * W;
+}
+
+// deterministic zonal sum of one row by one warp (fixed lane/iteration order)
+__device__ __forceinline__ float warp_row_sum(const float* row, int W, int lane) {
+  float s = 0.0f;
+  for (int x = lane; x < W; x += 32) s += row[x];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// means[pl][k], k = 0: global row 0, k = 1: global row H-1 of tensor `t` whose window is (row0, rows)
+__global__ void pole_means_kernel(const float* __restrict__ t, long long sB, int V, int rows, int row0,
+                                  int H, int W, int planes, float* __restrict__ means) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= planes * 2) return;
+  const int pl = warp >> 1, k = warp & 1;
+  const int gr = k ? H - 1 : 0, lr = gr - row0;
+  float m = 0.0f;
+  if (lr >= 0 && lr < rows) {
+    const float* row = plane_ptr(t, sB, V, rows, W, pl) + (long long)lr * W;
+    m = warp_row_sum(row, W, lane) / (float)W;
+  }
+  if (lane == 0) means[warp] = m;
+}
+
+// out rows 0 / H-1 <- their zonal mean (second enforce_pole_continuity, advection.py:169)
+__global__ void pole_rows_fix_kernel(float* __restrict__ t, int rows, int row0, int H, int W, int planes) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= planes * 2) return;
+  const int pl = warp >> 1, k = warp & 1;
+  const int gr = k ? H - 1 : 0, lr = gr - row0;
+  if (lr < 0 || lr >= rows) return;
+  float* row = t + ((long long)pl * rows + lr) * W;
+  const float m = warp_row_sum(row, W, lane) / (float)W;
+  __syncwarp();
+  for (int x = lane; x < W; x += 32) row[x] = m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int INTERP>
+__device__ __forceinline__ float sample(const Params& P, const float* __restrict__ f, const Traj& t,
+                                        float mean0, float mean1) {
+  constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
+  const float fx = floorf(t.ix), fy = floorf(t.iy);
+  const float tx = __fsub_rn(t.ix, fx), ty = __fsub_rn(t.iy, fy);
+  const int x0 = (int)fx + OMIN, y0 = (int)fy + OMIN;
+  float wx[NT], wy[NT], d0[NT], d1[NT];
+  axis_weights<INTERP, false>(tx, wx, d0);
+  axis_weights<INTERP, false>(ty, wy, d1);
+  float acc = 0.0f;
+  if (INTERP == 1) {
+    // ATen bilinear order: nw, ne, sw, se, weights formed first, FMA accumulate
+    const float v00 = tap_value(P, f, y0, x0, mean0, mean1), v01 = tap_value(P, f, y0, x0 + 1, mean0, mean1);
+    const float v10 = tap_value(P, f, y0 + 1, x0, mean0, mean1), v11 = tap_value(P, f, y0 + 1, x0 + 1, mean0, mean1);
+    acc = __fmul_rn(v00, __fmul_rn(wx[0], wy[0]));
+    acc = __fmaf_rn(v01, __fmul_rn(wx[1], wy[0]), acc);
+    acc = __fmaf_rn(v10, __fmul_rn(wx[0], wy[1]), acc);
+    acc = __fmaf_rn(v11, __fmul_rn(wx[1], wy[1]), acc);
+  } else {
+    // ATen bicubic: interpolate each row along x, then along y
+#pragma unroll
+    for (int a = 0; a < NT; ++a) {
+      float r = 0.0f;
+#pragma unroll
+      for (int b = 0; b < NT; ++b) r = __fmaf_rn(tap_value(P, f, y0 + a, x0 + b, mean0, mean1), wx[b], r);
+      acc = __fmaf_rn(r, wy[a], acc);
+    }
+  }
+  return acc;
+}
+
+template <bool EXACT, int INTERP, int VEC>
+__global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
+  const int pl = blockIdx.y;
+  const unsigned unit = blockIdx.x * blockDim.x + threadIdx.x;
+  if (unit >= (unsigned)(P.ownN * P.upr)) return;
+  const unsigned r = P.w4_mul ? fast_div(unit, P.w4_mul, P.w4_shift) : unit / (unsigned)P.upr;
+  const int x = (unit - r * P.upr) * VEC;
+  const int y = P.own0 + (int)r;  // global arrival row
+  const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
+  const float* f = plane_ptr(P.field, P.field_sB, P.V, P.fldN, P.W, pl);
+  const long long aoff = (long long)(y - P.arr0) * P.W + x;
+  const float* up = plane_ptr(P.u, P.u_sB, P.V, P.arrN, P.W, pl) + aoff;
+  const float* vp = plane_ptr(P.v, P.v_sB, P.V, P.arrN, P.W, pl) + aoff;
+  float mean0 = 0.0f, mean1 = 0.0f;
+  if (P.pole_fix) { mean0 = __ldg(P.fmean + 2 * pl); mean1 = __ldg(P.fmean + 2 * pl + 1); }
+  float uu[VEC], vv[VEC], ll[VEC], oo[VEC];
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(uu) = __ldcs(reinterpret_cast<const float4*>(up));
+    *reinterpret_cast<float4*>(vv) = __ldcs(reinterpret_cast<const float4*>(vp));
+    *reinterpret_cast<float4*>(ll) = __ldg(reinterpret_cast<const float4*>(P.lon + x));
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { uu[k] = __ldcs(up + k); vv[k] = __ldcs(vp + k); ll[k] = __ldg(P.lon + x + k); }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    Traj t;
+    trajectory<EXACT>(P, uu[k], vv[k], sp, cp, ll[k], t);
+    oo[k] = sample<INTERP>(P, f, t, mean0, mean1);
+  }
+  float* op = P.out + ((long long)pl * P.ownN + r) * P.W + x;
+  if (VEC == 4) __stcs(reinterpret_cast<float4*>(op), *reinterpret_cast<float4*>(oo));
+  else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) __stcs(op + k, oo[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, per arrival point: grad_u, grad_v and the row class of the departure cell
+// ---------------------------------------------------------------------------------------------
+template <int INTERP>
+__device__ __forceinline__ void sample_grad(const Params& P, const float* __restrict__ f, const Traj& t,
+                                            float mean0, float mean1, float& dx, float& dy) {
+  constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
+  const float fx = floorf(t.ix), fy = floorf(t.iy);
+  const float tx = __fsub_rn(t.ix, fx), ty = __fsub_rn(t.iy, fy);
+  const int x0 = (int)fx + OMIN, y0 = (int)fy + OMIN;
+  float wx[NT], wy[NT], dwx[NT], dwy[NT];
+  axis_weights<INTERP, true>(tx, wx, dwx);
+  axis_weights<INTERP, true>(ty, wy, dwy);
+  dx = 0.0f; dy = 0.0f;
+#pragma unroll
+  for (int a = 0; a < NT; ++a) {
+    float r = 0.0f, rd = 0.0f;
+#pragma unroll
+    for (int b = 0; b < NT; ++b) {
+      const float val = tap_value(P, f, y0 + a, x0 + b, mean0, mean1);
+      r = fmaf(val, wx[b], r);
+      rd = fmaf(val, dwx[b], rd);
+    }
+    dx = fmaf(rd, wy[a], dx);
+    dy = fmaf(r, dwy[a], dy);
+  }
+}
+
+// Jacobian of (ix, iy) w.r.t. (u, v): closed form of SURVEY 8a, validated in oracle/sl_oracle.py
+__device__ __forceinline__ void velocity_grads(const Params& P, const Traj& t, float sp, float cp, float gix,
+                                               float giy, float& gu, float& gv) {
+  const float r2 = fmaf(t.num, t.num, t.den * t.den);
+  const float inv_r2 = r2 > 0.0f ? 1.0f / r2 : 0.0f;
+  const float cacb = t.ca * t.cb, casb = t.ca * t.sb, sasb = t.sa * t.sb, sacb = t.sa * t.cb;
+  const float dlam_db = (t.den * cacb + t.num * casb * cp) * inv_r2;
+  const float dlam_da = (-t.den * sasb + t.num * fmaf(sacb, cp, t.ca * sp)) * inv_r2;
+  const bool inside = (t.s >= P.clamp_lo) && (t.s <= P.clamp_hi);
+  const float sc = fminf(fmaxf(t.s, P.clamp_lo), P.clamp_hi);
+  const float dphi_ds = inside ? rsqrtf(fmaf(-sc, sc, 1.0f)) : 0.0f;
+  const float ds_db = -casb * sp;
+  const float ds_da = fmaf(t.ca, cp, -sacb * sp);
+  const float kx = gix * P.Ax, ky = giy * P.Ay * dphi_ds;
+  gu = -P.dt * fmaf(kx, dlam_db, ky * ds_db);
+  gv = -P.dt * fmaf(kx, dlam_da, ky * ds_da);
+}
+
+template <bool EXACT, int INTERP, int VEC>
+__global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
+  const int pl = blockIdx.y;
+  const unsigned unit = blockIdx.x * blockDim.x + threadIdx.x;
+  int reach = 0;
+  if (unit < (unsigned)(P.arrN * P.upr)) {
+    const unsigned r = P.w4_mul ? fast_div(unit, P.w4_mul, P.w4_shift) : unit / (unsigned)P.upr;
+    const int x = (unit - r * P.upr) * VEC;
+    const int y = P.arr0 + (int)r;  // global arrival row
+    const bool own = (y >= P.own0) && (y < P.own0 + P.ownN) && (P.gu != nullptr);
+    const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
+    const long long aoff = (long long)r * P.W + x;
+    const float* up = plane_ptr(P.u, P.u_sB, P.V, P.arrN, P.W, pl) + aoff;
+    const float* vp = plane_ptr(P.v, P.v_sB, P.V, P.arrN, P.W, pl) + aoff;
+    float uu[VEC], vv[VEC], ll[VEC], gg[VEC], ou[VEC], ov[VEC];
+    signed char cc[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(uu) = __ldg(reinterpret_cast<const float4*>(up));
+      *reinterpret_cast<float4*>(vv) = __ldg(reinterpret_cast<const float4*>(vp));
+      *reinterpret_cast<float4*>(ll) = __ldg(reinterpret_cast<const float4*>(P.lon + x));
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { uu[k] = __ldg(up + k); vv[k] = __ldg(vp + k); ll[k] = __ldg(P.lon + x + k); }
+    }
+    const float* f = nullptr;
+    float mean0 = 0.0f, mean1 = 0.0f;
+    if (own) {
+      f = plane_ptr(P.field, P.field_sB, P.V, P.fldN, P.W, pl);
+      const float* gp = plane_ptr(P.gout, P.gout_sB, P.V, P.arrN, P.W, pl) + aoff;
+      if (VEC == 4) *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(gp));
+      else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) gg[k] = __ldg(gp + k);
+      }
+      if (P.pole_fix) {
+        mean0 = __ldg(P.fmean + 2 * pl); mean1 = __ldg(P.fmean + 2 * pl + 1);
+        if (y == 0 || y == P.H - 1) {  // adjoint of the output pole mean
+          const float gm = __ldg(P.gmean + 2 * pl + (y == 0 ? 0 : 1));
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) gg[k] = gm;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      Traj t;
+      trajectory<EXACT>(P, uu[k], vv[k], sp, cp, ll[k], t);
+      int c = (int)floorf(t.iy) - (y + P.p);
+      const int ac = abs(c);
+      if (ac > PARADIS_SL_MAX_DISP_ROWS) {
+        if (P.status) *P.status = PARADIS_ERR_DISPLACEMENT;
+        c = c > 0 ? 127 : -127;
+      }
+      reach = max(reach, min(ac, 127));
+      cc[k] = (signed char)c;
+      if (own) {
+        float dx, dy;
+        sample_grad<INTERP>(P, f, t, mean0, mean1, dx, dy);
+        velocity_grads(P, t, sp, cp, gg[k] * dx, gg[k] * dy, ou[k], ov[k]);
+      }
+    }
+    if (P.cls) {
+      signed char* cp8 = P.cls + ((long long)pl * P.arrN + r) * P.W + x;
+      if (VEC == 4) *reinterpret_cast<char4*>(cp8) = make_char4(cc[0], cc[1], cc[2], cc[3]);
+      else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) cp8[k] = cc[k];
+      }
+    }
+    if (own) {
+      const long long ooff = ((long long)pl * P.ownN + (y - P.own0)) * P.W + x;
+      if (VEC == 4) {
+        __stcs(reinterpret_cast<float4*>(P.gu + ooff), *reinterpret_cast<float4*>(ou));
+        __stcs(reinterpret_cast<float4*>(P.gv + ooff), *reinterpret_cast<float4*>(ov));
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { __stcs(P.gu + ooff + k, ou[k]); __stcs(P.gv + ooff + k, ov[k]); }
+      }
+    }
+  }
+  if (P.blkmax) {  // per-block maximum, no atomics: warp max -> smem -> thread 0
+    __shared__ int smax[8];
+    reach = __reduce_max_sync(0xffffffffu, reach);
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = reach;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int m = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = max(m, smax[w]);
+      P.blkmax[(long long)pl * P.nblk + blockIdx.x] = (unsigned char)m;
+    }
+  }
+}
+
+__global__ void plane_reach_kernel(const unsigned char* __restrict__ blkmax, int nblk, int planes,
+                                   int* __restrict__ plane_reach) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= planes) return;
+  int m = 0;
+  for (int i = lane; i < nblk; i += 32) m = max(m, (int)blkmax[(long long)warp * nblk + i]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if (lane == 0) plane_reach[warp] = m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, grad_field: gather over inverse stencils.
+//
+// One warp owns one output row (plane, r) and a private accumulator acc[W] in shared memory.
+// It visits, in a fixed order, every padded destination row Rd that folds onto r through the
+// GeoCyclic map (r itself, plus a reflected cap row when r is within p rows of a pole).  For each
+// Rd it scans the row classes of the arrival rows that can reach Rd, compacts the matching arrival
+// points (ballot/popc, raster order) into a small queue and, 32 at a time, recomputes their
+// trajectory and adds their weights into acc.  Lanes that hit the same column are combined in lane
+// order by the lowest lane (match_any + shuffles), so every add into acc has a single writer and a
+// data-independent order: deterministic, no atomics.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGatherWarps = 8;
+constexpr int kQueue = 160;  // >= 31 + 128
+
+template <bool EXACT, int INTERP>
+__device__ __forceinline__ void gather_chunk(const Params& P, int pl, int Rd, int shift, float* acc,
+                                             const unsigned* queue, int n, int lane) {
+  constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
+  float c[NT];
+#pragma unroll
+  for (int b = 0; b < NT; ++b) c[b] = 0.0f;
+  int key = -1 - lane;  // idle lanes: unique keys, zero contributions
+  int xb = 0;
+  if (lane < n) {
+    const unsigned e = queue[lane];
+    const int y = (int)(e >> 16), x = (int)(e & 0xffffu);  // global arrival row, column
+    const long long aoff = (long long)(y - P.arr0) * P.W + x;
+    const float uu = __ldg(plane_ptr(P.u, P.u_sB, P.V, P.arrN, P.W, pl) + aoff);
+    const float vv = __ldg(plane_ptr(P.v, P.v_sB, P.V, P.arrN, P.W, pl) + aoff);
+    float g;
+    if (P.pole_fix && (y == 0 || y == P.H - 1)) g = __ldg(P.gmean + 2 * pl + (y == 0 ? 0 : 1));
+    else g = __ldg(plane_ptr(P.gout, P.gout_sB, P.V, P.arrN, P.W, pl) + aoff);
+    Traj t;
+    trajectory<EXACT>(P, uu, vv, __ldg(P.sin_lat + y), __ldg(P.cos_lat + y), __ldg(P.lon + x), t);
+    const float fx = floorf(t.ix), fy = floorf(t.iy);
+    const float tx = __fsub_rn(t.ix, fx), ty = __fsub_rn(t.iy, fy);
+    const int a = Rd - ((int)fy + OMIN);  // which y-tap of this point lands on Rd
+    if (a >= 0 && a < NT) {
+      float wx[NT], wy[NT], d0[NT], d1[NT];
+      axis_weights<INTERP, false>(tx, wx, d0);
+      axis_weights<INTERP, false>(ty, wy, d1);
+      float wya = wy[0];
+#pragma unroll
+      for (int k = 1; k < NT; ++k) wya = (a == k) ? wy[k] : wya;
+      const float val = g * wya;
+      xb = (int)fx + OMIN;  // padded column of tap 0
+#pragma unroll
+      for (int b = 0; b < NT; ++b) c[b] = ((unsigned)(xb + b) < (unsigned)P.Wp) ? val * wx[b] : 0.0f;
+      // fold the column through the GeoCyclic map once, at the key level
+      int j = xb - P.p - shift;  // in [-p - 1 - W/2, W + p) for any finite trajectory
+      if (j < 0) j += P.W;
+      else if (j >= P.W) j -= P.W;
+      if ((unsigned)j < (unsigned)P.W) key = j;
+      else {
+#pragma unroll
+        for (int b = 0; b < NT; ++b) c[b] = 0.0f;  // non-finite coordinates: every tap is out of bounds
+      }
+    }
+  }
+  // combine lanes with the same base column, ascending lane order, lowest lane writes
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  const int leader = __ffs(peers) - 1;
+  const int npeer = __popc(peers);
+  const int nmax = __reduce_max_sync(0xffffffffu, npeer);
+  unsigned rest = peers & (peers - 1);  // peers without the leader
+  for (int rr = 1; rr < nmax; ++rr) {
+    const int src = rest ? __ffs(rest) - 1 : lane;
+    const bool take = (lane == leader) && rest;
+    rest &= rest - 1;
+#pragma unroll
+    for (int b = 0; b < NT; ++b) {
+      const float o = __shfl_sync(0xffffffffu, c[b], src);
+      if (take) c[b] += o;
+    }
+  }
+  const bool writer = (lane == leader) && (key >= 0);
+#pragma unroll
+  for (int b = 0; b < NT; ++b) {
+    if (writer) {
+      int j = key + b;
+      if (j >= P.W) j -= P.W;
+      acc[j] += c[b];
+    }
+    __syncwarp();
+  }
+}
+
+template <bool EXACT, int INTERP>
+__global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const Params P) {
+  constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pl = blockIdx.y;
+  const int lr = blockIdx.x * kGatherWarps + warp;  // local output row
+  if (lr >= P.ownN) return;
+  const int r = P.own0 + lr;                         // global output row
+  float* acc = smem + (size_t)warp * (P.W + kQueue);
+  unsigned* queue = reinterpret_cast<unsigned*>(acc + P.W);
+  for (int x = lane; x < P.W; x += 32) acc[x] = 0.0f;
+  __syncwarp();
+  const int reach = P.plane_reach[pl];
+  const signed char* cls = P.cls + (long long)pl * P.arrN * P.W;
+
+  // destination rows (padded coordinates) folding onto r: itself, north cap, south cap
+  for (int src = 0; src < 3; ++src) {
+    int Rd, shift;
+    if (src == 0) { Rd = r + P.p; shift = 0; }
+    else if (src == 1) { if (r < 1 || r > P.p) continue; Rd = P.p - r; shift = P.halfW; }
+    else { const int i = 2 * (P.H - 1) - r; if (i < P.H || i >= P.H + P.p) continue; Rd = i + P.p; shift = P.halfW; }
+    // arrival rows y with floor(iy) + OMIN <= Rd <= floor(iy) + OMIN + NT - 1, floor(iy) = y + p + class
+    int ylo = Rd - P.p - (OMIN + NT - 1) - reach, yhi = Rd - P.p - OMIN + reach;
+    ylo = max(ylo, P.arr0); yhi = min(yhi, P.arr0 + P.arrN - 1);
+    int qn = 0;
+    for (int y = ylo; y <= yhi; ++y) {
+      const signed char* crow = cls + (long long)(y - P.arr0) * P.W;
+      const int cbase = Rd - (y + P.p) - OMIN;  // tap index a = cbase - class must be in [0, NT)
+      for (int x0 = 0; x0 < P.W; x0 += 128) {
+        const int x = x0 + lane * 4;
+        unsigned m4 = 0;
+        if (x + 3 < P.W && (P.W & 3) == 0) {
+          const char4 q = *reinterpret_cast<const char4*>(crow + x);
+          m4 |= ((unsigned)(cbase - q.x) < (unsigned)NT) ? 1u : 0u;
+          m4 |= ((unsigned)(cbase - q.y) < (unsigned)NT) ? 2u : 0u;
+          m4 |= ((unsigned)(cbase - q.z) < (unsigned)NT) ? 4u : 0u;
+          m4 |= ((unsigned)(cbase - q.w) < (unsigned)NT) ? 8u : 0u;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (x + k < P.W && (unsigned)(cbase - crow[x + k]) < (unsigned)NT) m4 |= 1u << k;
+        }
+        // raster-order compaction: position = matches in lower lanes + lower bits of own mask
+        const unsigned b0 = __ballot_sync(0xffffffffu, m4 & 1u), b1 = __ballot_sync(0xffffffffu, m4 & 2u);
+        const unsigned b2 = __ballot_sync(0xffffffffu, m4 & 4u), b3 = __ballot_sync(0xffffffffu, m4 & 8u);
+        const unsigned lt = (1u << lane) - 1u;
+        int pos = qn + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (m4 & (1u << k)) queue[pos++] = ((unsigned)y << 16) | (unsigned)(x + k);
+        qn += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+        __syncwarp();
+        int head = 0;
+        while (qn - head >= 32) {
+          gather_chunk<EXACT, INTERP>(P, pl, Rd, shift, acc, queue + head, 32, lane);
+          head += 32;
+        }
+        if (head) {  // move the tail (< 32 entries) to the front
+          const int rem = qn - head;
+          unsigned e = 0;
+          if (lane < rem) e = queue[head + lane];
+          __syncwarp();
+          if (lane < rem) queue[lane] = e;
+          __syncwarp();
+          qn = rem;
+        }
+      }
+    }
+    if (qn) gather_chunk<EXACT, INTERP>(P, pl, Rd, shift, acc, queue, qn, lane);
+  }
+  // adjoint of the first enforce_pole_continuity (advection.py:129): pole rows get their mean
+  float* orow = P.gfield + ((long long)pl * P.ownN + lr) * P.W;
+  if (P.pole_fix && (r == 0 || r == P.H - 1)) {
+    const float m = warp_row_sum(acc, P.W, lane) / (float)P.W;
+    for (int x = lane; x < P.W; x += 32) orow[x] = m;
+  } else {
+    for (int x = lane; x < P.W; x += 32) orow[x] = acc[x];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone GeoCyclic padding (model/padding.py:11-39) and its adjoint
+// ---------------------------------------------------------------------------------------------
+__global__ void geocyclic_pad_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int p) {
+  const int Hp = H + 2 * p, Wp = W + 2 * p;
+  const long long pl = blockIdx.z;
+  const int R = blockIdx.y;
+  int i = R - p, shift = 0;
+  if (i < 0) { i = -i; shift = W / 2; }
+  else if (i >= H) { i = 2 * (H - 1) - i; shift = W / 2; }
+  const float* src = x + (pl * H + i) * W;
+  float* dst = y + (pl * Hp + R) * Wp;
+  for (int C = blockIdx.x * blockDim.x + threadIdx.x; C < Wp; C += gridDim.x * blockDim.x) {
+    int j = C - p - shift;
+    if (j < 0) j += W; else if (j >= W) j -= W;
+    dst[C] = __ldg(src + j);
+  }
+}
+
+// gx[i, j] = sum of every padded cell whose source is (i, j); fixed order: interior row first,
+// then north cap, then south cap; within a row: centre, left wrap, right wrap.
+__global__ void geocyclic_pad_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int H, int W, int p) {
+  const int Hp = H + 2 * p, Wp = W + 2 * p;
+  const long long pl = blockIdx.z;
+  const int i = blockIdx.y;
+  const float* g = gy + pl * (long long)Hp * Wp;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < W; j += gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int src = 0; src < 3; ++src) {
+      int R, shift;
+      if (src == 0) { R = i + p; shift = 0; }
+      else if (src == 1) { if (i < 1 || i > p) continue; R = p - i; shift = W / 2; }
+      else { const int ii = 2 * (H - 1) - i; if (ii < H || ii >= H + p) continue; R = ii + p; shift = W / 2; }
+      // padded columns C with (C - p - shift) mod W == j
+      int c = j + shift; if (c >= W) c -= W;   // C - p in [0, W)
+      const float* row = g + (long long)R * Wp + p;
+      s += row[c];
+      if (c >= W - p) s += row[c - W];         // left wrap columns  C - p in [-p, 0)
+      if (c < p) s += row[c + W];              // right wrap columns C - p in [W, W + p)
+    }
+    gx[(pl * H + i) * W + j] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int fill_params(Params& P, const paradis_sl_geom* g, int B, int V, float dt, int interp, int pole_fix) {
+  if (!g) return fail(PARADIS_ERR_NULL_POINTER, "geom is NULL");
+  if (!g->sin_lat || !g->cos_lat || !g->lon) return fail(PARADIS_ERR_NULL_POINTER, "geom tables are NULL");
+  if (interp != PARADIS_INTERP_BILINEAR && interp != PARADIS_INTERP_BICUBIC)
+    return fail(PARADIS_ERR_BAD_INTERP, "interp must be 1 (bilinear) or 2 (bicubic), got %d", interp);
+  const int p = interp;
+  if (B <= 0 || V <= 0 || g->H <= 0 || g->W <= 0) return fail(PARADIS_ERR_BAD_SHAPE, "non-positive dimension");
+  if (g->W % 2) return fail(PARADIS_ERR_ODD_WIDTH, "Number of longitude points must be even (W=%d)", g->W);
+  if (g->H < p + 2) return fail(PARADIS_ERR_BAD_SHAPE, "H=%d too small for padding %d", g->H, p);
+  if (g->H > 65535 || g->W > 65535) return fail(PARADIS_ERR_BAD_SHAPE, "mesh larger than 65535 not supported");
+  if ((long long)B * V > 65535) return fail(PARADIS_ERR_BAD_SHAPE, "B*V=%lld exceeds 65535 planes per call", (long long)B * V);
+  auto inside = [&](int r0, int n) { return n > 0 && r0 >= 0 && r0 + n <= g->H; };
+  if (!inside(g->own_row0, g->own_rows) || !inside(g->arr_row0, g->arr_rows) || !inside(g->fld_row0, g->fld_rows))
+    return fail(PARADIS_ERR_BAD_SHAPE, "row window outside the mesh");
+  if (g->arr_row0 > g->own_row0 || g->arr_row0 + g->arr_rows < g->own_row0 + g->own_rows)
+    return fail(PARADIS_ERR_BAD_SHAPE, "arr window must contain own window");
+  memset(&P, 0, sizeof(P));
+  P.H = g->H; P.W = g->W; P.p = p; P.Hp = g->H + 2 * p; P.Wp = g->W + 2 * p; P.halfW = g->W / 2;
+  P.own0 = g->own_row0; P.ownN = g->own_rows; P.arr0 = g->arr_row0; P.arrN = g->arr_rows;
+  P.fld0 = g->fld_row0; P.fldN = g->fld_rows;
+  P.sin_lat = g->sin_lat; P.cos_lat = g->cos_lat; P.lon = g->lon;
+  P.min_lat = g->min_lat; P.d_lat = g->d_lat; P.min_lon = g->min_lon; P.d_lon = g->d_lon;
+  P.dt = dt;
+  P.Wm1 = (float)g->W - 1.0f; P.Hm1 = (float)g->H - 1.0f;
+  P.Wpm1 = (float)(P.Wp - 1); P.Hpm1 = (float)(P.Hp - 1); P.pf = (float)p;
+  P.Ax = P.Wm1 / g->d_lon; P.Ay = P.Hm1 / g->d_lat;
+  P.Cx = (float)((double)p - (double)g->min_lon * (double)P.Ax);
+  P.Cy = (float)((double)p - (double)g->min_lat * (double)P.Ay);
+  P.clamp_lo = (float)(-1 + 1e-7); P.clamp_hi = (float)(1 - 1e-7);
+  P.B = B; P.V = V; P.pole_fix = pole_fix ? 1 : 0;
+  return PARADIS_OK;
+}
+
+static void set_units(Params& P, int vec, int rows) {
+  P.upr = P.W / vec;
+  P.w4_mul = 0; P.w4_shift = 0;
+  // n / upr == umulhi(n, ceil(2^32 / upr)) for n * upr < 2^32
+  const unsigned long long n_max = (unsigned long long)rows * P.upr;
+  if (P.upr > 1 && n_max * P.upr < (1ull << 32)) P.w4_mul = (unsigned)(((1ull << 32) + P.upr - 1) / P.upr);
+}
+
+static bool aligned16(const void* ptr) { return ((uintptr_t)ptr & 15u) == 0; }
+
+extern "C" size_t paradis_sl_advect_fwd_workspace(int B, int V) {
+  return align_up((size_t)B * V * 2 * sizeof(float), 256);
+}
+
+template <bool EXACT, int INTERP>
+static void launch_fwd(const Params& P, int vec, dim3 grid, cudaStream_t st) {
+  if (vec == 4) sl_fwd_kernel<EXACT, INTERP, 4><<<grid, 256, 0, st>>>(P);
+  else sl_fwd_kernel<EXACT, INTERP, 1><<<grid, 256, 0, st>>>(P);
+}
+
+extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* field, const float* u,
+                                     const float* v, float* out, int B, int V, int64_t field_sB, int64_t u_sB,
+                                     int64_t v_sB, float dt, int interp, int pole_fix, int math, void* workspace,
+                                     size_t workspace_bytes, int32_t* status, void* stream) {
+  Params P;
+  if (int rc = fill_params(P, geom, B, V, dt, interp, pole_fix)) return rc;
+  if (!field || !u || !v || !out) return fail(PARADIS_ERR_NULL_POINTER, "NULL tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int planes = B * V;
+  P.field = field; P.u = u; P.v = v; P.out = out;
+  P.field_sB = field_sB; P.u_sB = u_sB; P.v_sB = v_sB;
+  P.status = status;
+  if (pole_fix) {
+    if (!workspace || workspace_bytes < paradis_sl_advect_fwd_workspace(B, V))
+      return fail(PARADIS_ERR_WORKSPACE, "forward workspace too small (%zu bytes)", workspace_bytes);
+    float* fmean = (float*)workspace;
+    P.fmean = fmean;
+    const int warps = planes * 2;
+    pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(field, field_sB, V, P.fldN, P.fld0, P.H, P.W, planes, fmean);
+  }
+  const bool vec_ok = (P.W % 4 == 0) && aligned16(field) && aligned16(u) && aligned16(v) && aligned16(out) &&
+                      aligned16(P.lon) && (u_sB % 4 == 0) && (v_sB % 4 == 0);
+  const int vec = vec_ok ? 4 : 1;
+  set_units(P, vec, P.ownN);
+  const unsigned units = (unsigned)P.ownN * P.upr;
+  dim3 grid((units + 255) / 256, planes);
+  const bool exact = math == PARADIS_MATH_EXACT;
+  if (interp == 1) { if (exact) launch_fwd<true, 1>(P, vec, grid, st); else launch_fwd<false, 1>(P, vec, grid, st); }
+  else             { if (exact) launch_fwd<true, 2>(P, vec, grid, st); else launch_fwd<false, 2>(P, vec, grid, st); }
+  if (pole_fix) {
+    const int warps = planes * 2;
+    pole_rows_fix_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(out, P.ownN, P.own0, P.H, P.W, planes);
+  }
+  return check_launch("paradis_sl_advect_fwd");
+}
+
+// workspace layout (backward): fmean | gmean | plane_reach | blkmax | cls
+struct BwdWs { size_t fmean, gmean, reach, blkmax, cls, total; int nblk; };
+static BwdWs bwd_layout(int B, int V, int arr_rows, int W) {
+  BwdWs w;
+  const size_t planes = (size_t)B * V;
+  // blocks per plane of the arrival kernel in the worst case (VEC = 1)
+  w.nblk = (int)(((size_t)arr_rows * W + 255) / 256);
+  size_t off = 0;
+  w.fmean = off; off += align_up(planes * 2 * sizeof(float), 256);
+  w.gmean = off; off += align_up(planes * 2 * sizeof(float), 256);
+  w.reach = off; off += align_up(planes * sizeof(int), 256);
+  w.blkmax = off; off += align_up(planes * (size_t)w.nblk, 256);
+  w.cls = off; off += align_up(planes * (size_t)arr_rows * W, 256);
+  w.total = off;
+  return w;
+}
+
+extern "C" size_t paradis_sl_advect_bwd_workspace(int B, int V, int arr_rows, int W) {
+  return bwd_layout(B, V, arr_rows, W).total;
+}
+
+template <bool EXACT, int INTERP>
+static int launch_bwd(Params& P, int vec, cudaStream_t st, bool want_field) {
+  const int planes = P.B * P.V;
+  set_units(P, vec, P.arrN);
+  const unsigned units = (unsigned)P.arrN * P.upr;
+  dim3 grid((units + 255) / 256, planes);
+  if ((int)grid.x > P.nblk) return fail(PARADIS_ERR_WORKSPACE, "internal: blkmax layout");
+  P.nblk = grid.x;
+  if (vec == 4) sl_bwd_arrival_kernel<EXACT, INTERP, 4><<<grid, 256, 0, st>>>(P);
+  else sl_bwd_arrival_kernel<EXACT, INTERP, 1><<<grid, 256, 0, st>>>(P);
+  if (!want_field) return PARADIS_OK;
+  plane_reach_kernel<<<(planes * 32 + 255) / 256, 256, 0, st>>>(P.blkmax, P.nblk, planes, P.plane_reach);
+  const size_t smem = (size_t)kGatherWarps * (P.W + kQueue) * sizeof(float);
+  if (smem > 227 * 1024) return fail(PARADIS_ERR_BAD_SHAPE, "W=%d too wide for the gather kernel's shared memory", P.W);
+  auto kern = sl_bwd_gather_kernel<EXACT, INTERP>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(PARADIS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  dim3 ggrid((P.ownN + kGatherWarps - 1) / kGatherWarps, planes);
+  kern<<<ggrid, kGatherWarps * 32, smem, st>>>(P);
+  return PARADIS_OK;
+}
+
+extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* grad_out, const float* field,
+                                     const float* u, const float* v, float* grad_field, float* grad_u,
+                                     float* grad_v, int B, int V, int64_t gout_sB, int64_t field_sB, int64_t u_sB,
+                                     int64_t v_sB, float dt, int interp, int pole_fix, int math, void* workspace,
+                                     size_t workspace_bytes, int32_t* status, void* stream) {
+  Params P;
+  if (int rc = fill_params(P, geom, B, V, dt, interp, pole_fix)) return rc;
+  if (!grad_out || !field || !u || !v) return fail(PARADIS_ERR_NULL_POINTER, "NULL tensor pointer");
+  if ((grad_u == nullptr) != (grad_v == nullptr)) return fail(PARADIS_ERR_NULL_POINTER, "grad_u and grad_v must both be given or both be NULL");
+  const BwdWs L = bwd_layout(B, V, P.arrN, P.W);
+  if (!workspace || workspace_bytes < L.total)
+    return fail(PARADIS_ERR_WORKSPACE, "backward workspace too small (%zu < %zu bytes)", workspace_bytes, L.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int planes = B * V;
+  char* ws = (char*)workspace;
+  float* fmean = (float*)(ws + L.fmean);
+  float* gmean = (float*)(ws + L.gmean);
+  P.field = field; P.u = u; P.v = v; P.gout = grad_out;
+  P.gfield = grad_field; P.gu = grad_u; P.gv = grad_v;
+  P.field_sB = field_sB; P.u_sB = u_sB; P.v_sB = v_sB; P.gout_sB = gout_sB;
+  P.status = status;
+  P.fmean = fmean; P.gmean = gmean;
+  P.plane_reach = (int*)(ws + L.reach);
+  P.blkmax = grad_field ? (unsigned char*)(ws + L.blkmax) : nullptr;
+  P.cls = grad_field ? (signed char*)(ws + L.cls) : nullptr;
+  P.nblk = L.nblk;
+  if (pole_fix) {
+    const int warps = planes * 2;
+    pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(field, field_sB, V, P.fldN, P.fld0, P.H, P.W, planes, fmean);
+    pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(grad_out, gout_sB, V, P.arrN, P.arr0, P.H, P.W, planes, gmean);
+  }
+  const bool vec_ok = (P.W % 4 == 0) && aligned16(field) && aligned16(u) && aligned16(v) && aligned16(grad_out) &&
+                      aligned16(P.lon) && (!grad_u || (aligned16(grad_u) && aligned16(grad_v))) &&
+                      (u_sB % 4 == 0) && (v_sB % 4 == 0) && (gout_sB % 4 == 0);
+  const int vec = vec_ok ? 4 : 1;
+  const bool exact = math == PARADIS_MATH_EXACT;
+  int rc;
+  if (interp == 1) rc = exact ? launch_bwd<true, 1>(P, vec, st, grad_field != nullptr) : launch_bwd<false, 1>(P, vec, st, grad_field != nullptr);
+  else             rc = exact ? launch_bwd<true, 2>(P, vec, st, grad_field != nullptr) : launch_bwd<false, 2>(P, vec, st, grad_field != nullptr);
+  if (rc) return rc;
+  return check_launch("paradis_sl_advect_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// padding op
+// ---------------------------------------------------------------------------------------------
+static int pad_check(const void* a, const void* b, int64_t planes, int H, int W, int p) {
+  if (!a || !b) return fail(PARADIS_ERR_NULL_POINTER, "NULL tensor pointer");
+  if (planes <= 0 || H <= 0 || W <= 0 || p < 0) return fail(PARADIS_ERR_BAD_SHAPE, "non-positive dimension");
+  if (W % 2) return fail(PARADIS_ERR_ODD_WIDTH, "Number of longitude points must be even (W=%d)", W);
+  if (H < p + 1 || W < 2 * p) return fail(PARADIS_ERR_BAD_SHAPE, "pad width %d too large for %dx%d", p, H, W);
+  if (planes > 65535 || H + 2 * p > 65535) return fail(PARADIS_ERR_BAD_SHAPE, "too many planes/rows for one launch");
+  return PARADIS_OK;
+}
+
+extern "C" int paradis_geocyclic_pad_fwd(const float* x, float* y, int64_t planes, int H, int W, int p, void* stream) {
+  if (int rc = pad_check(x, y, planes, H, W, p)) return rc;
+  const int Wp = W + 2 * p;
+  dim3 grid((Wp + 255) / 256, H + 2 * p, (unsigned)planes);
+  geocyclic_pad_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, H, W, p);
+  return check_launch("paradis_geocyclic_pad_fwd");
+}
+
+extern "C" int paradis_geocyclic_pad_bwd(const float* gy, float* gx, int64_t planes, int H, int W, int p, void* stream) {
+  if (int rc = pad_check(gy, gx, planes, H, W, p)) return rc;
+  dim3 grid((W + 255) / 256, H, (unsigned)planes);
+  geocyclic_pad_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gy, gx, H, W, p);
+  return check_launch("paradis_geocyclic_pad_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer entry: chunks of planes pipelined over three streams (H2D | kernels | D2H overlap
+// across chunks because consecutive chunks live on different streams and slots)
+// ---------------------------------------------------------------------------------------------
+static constexpr int kSlots = 3;
+
+struct HostSlot { size_t field, u, v, gout, out, gfield, gu, gv, wsf, wsb, status, total; };
+static HostSlot host_slot_layout(int H, int W, int c) {
+  HostSlot s;
+  const size_t t = align_up((size_t)c * H * W * sizeof(float), 256);
+  size_t off = 0;
+  s.field = off; off += t; s.u = off; off += t; s.v = off; off += t; s.gout = off; off += t;
+  s.out = off; off += t; s.gfield = off; off += t; s.gu = off; off += t; s.gv = off; off += t;
+  s.wsf = off; off += paradis_sl_advect_fwd_workspace(1, c);
+  s.wsb = off; off += paradis_sl_advect_bwd_workspace(1, c, H, W);
+  s.status = off; off += 256;
+  s.total = off;
+  return s;
+}
+
+extern "C" size_t paradis_sl_host_scratch_bytes(int H, int W, int chunk_planes) {
+  if (H <= 0 || W <= 0 || chunk_planes <= 0) return 0;
+  return host_slot_layout(H, W, chunk_planes).total * kSlots;
+}
+
+extern "C" int paradis_sl_advect_fwd_bwd_host(const paradis_sl_geom* geom, const float* h_field, const float* h_u,
+                                              const float* h_v, const float* h_grad_out, float* h_out,
+                                              float* h_grad_field, float* h_grad_u, float* h_grad_v, int64_t planes,
+                                              float dt, int interp, int pole_fix, int math, int chunk_planes,
+                                              void* d_scratch, size_t scratch_bytes) {
+  if (!geom) return fail(PARADIS_ERR_NULL_POINTER, "geom is NULL");
+  if (!h_field || !h_u || !h_v || !h_grad_out || !h_out || !h_grad_field || !h_grad_u || !h_grad_v)
+    return fail(PARADIS_ERR_NULL_POINTER, "NULL host pointer");
+  if (planes <= 0 || chunk_planes <= 0) return fail(PARADIS_ERR_BAD_SHAPE, "non-positive plane count");
+  const int H = geom->H, W = geom->W;
+  if (geom->own_row0 != 0 || geom->own_rows != H || geom->arr_rows != H || geom->fld_rows != H)
+    return fail(PARADIS_ERR_BAD_SHAPE, "host entry works on the full mesh");
+  const HostSlot L = host_slot_layout(H, W, chunk_planes);
+  if (!d_scratch || scratch_bytes < L.total * kSlots)
+    return fail(PARADIS_ERR_WORKSPACE, "host-entry scratch too small (%zu < %zu bytes)", scratch_bytes, L.total * kSlots);
+  cudaStream_t st[kSlots];
+  for (int i = 0; i < kSlots; ++i)
+    if (cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess)
+      return fail(PARADIS_ERR_CUDA, "cudaStreamCreate failed");
+  int rc = PARADIS_OK;
+  const size_t plane_elems = (size_t)H * W;
+  int64_t done = 0;
+  for (int it = 0; done < planes && rc == PARADIS_OK; ++it) {
+    const int c = (int)((planes - done < chunk_planes) ? planes - done : chunk_planes);
+    const int slot = it % kSlots;
+    char* base = (char*)d_scratch + (size_t)slot * L.total;
+    cudaStream_t s = st[slot];
+    const size_t bytes = (size_t)c * plane_elems * sizeof(float), off = (size_t)done * plane_elems;
+    float *df = (float*)(base + L.field), *du = (float*)(base + L.u), *dv = (float*)(base + L.v),
+          *dg = (float*)(base + L.gout), *dout = (float*)(base + L.out), *dgf = (float*)(base + L.gfield),
+          *dgu = (float*)(base + L.gu), *dgv = (float*)(base + L.gv);
+    cudaMemcpyAsync(df, h_field + off, bytes, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(du, h_u + off, bytes, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(dv, h_v + off, bytes, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(dg, h_grad_out + off, bytes, cudaMemcpyHostToDevice, s);
+    const int64_t sB = (int64_t)c * plane_elems;
+    rc = paradis_sl_advect_fwd(geom, df, du, dv, dout, 1, c, sB, sB, sB, dt, interp, pole_fix, math, base + L.wsf,
+                               paradis_sl_advect_fwd_workspace(1, c), nullptr, s);
+    if (rc) break;
+    cudaMemcpyAsync(h_out + off, dout, bytes, cudaMemcpyDeviceToHost, s);
+    rc = paradis_sl_advect_bwd(geom, dg, df, du, dv, dgf, dgu, dgv, 1, c, sB, sB, sB, sB, dt, interp, pole_fix, math,
+                               base + L.wsb, paradis_sl_advect_bwd_workspace(1, c, H, W), nullptr, s);
+    if (rc) break;
+    cudaMemcpyAsync(h_grad_field + off, dgf, bytes, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(h_grad_u + off, dgu, bytes, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(h_grad_v + off, dgv, bytes, cudaMemcpyDeviceToHost, s);
+    done += c;
+  }
+  for (int i = 0; i < kSlots; ++i) {
+    cudaError_t e = cudaStreamSynchronize(st[i]);
+    if (e != cudaSuccess && rc == PARADIS_OK) rc = fail(PARADIS_ERR_CUDA, "host entry: %s", cudaGetErrorString(e));
+    cudaStreamDestroy(st[i]);
+  }
+  return rc;
+}

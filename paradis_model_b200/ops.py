@@ -1,0 +1,335 @@
+"""torch.library custom ops over the C ABI (include/paradis_sl.h).
+
+Ops (namespace ``paradis``)
+    sl_advect / sl_advect_backward      model/advection.py:129-169, fused
+    geocyclic_pad / geocyclic_pad_backward   model/padding.py:11-39
+
+Each op has a fake (meta) implementation and an autograd formula, so it works under
+``torch.compile(fullgraph=True)``, non-reentrant activation checkpointing (nothing but
+the inputs is saved; the trajectory is recomputed in backward) and bf16 autocast (inputs
+are cast to fp32, as torch's own autocast policy does for grid_sampler / asin / atan2).
+CUDA only: there is no CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+__all__ = ["SLGeometry", "sl_advect", "geocyclic_pad", "check_status", "host_fwd_bwd"]
+
+_status_words: dict = {}
+
+
+def _status_word(device: torch.device) -> Tensor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _status_words:
+        _status_words[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _status_words[key]
+
+
+def check_status(device=None) -> None:
+    """Synchronise and raise if a kernel flagged a device-side contract violation
+    (displacement above 126 rows, or a departure stencil outside the rows held by
+    ``field`` in a latitude-band call)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    word = _status_word(device)
+    code = int(word.item())
+    if code:
+        word.zero_()
+        raise RuntimeError(f"paradis_sl device status {_lib.STATUS_NAMES.get(code, code)}: "
+                           "semi-Lagrangian displacement outside the supported window")
+
+
+def _stream(t: Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _inner_contig(t: Tensor) -> Tensor:
+    """Accept batch-strided views (model/paradis.py:235-237) without copying."""
+    _, V, R, W = t.shape
+    if t.stride(3) == 1 and t.stride(2) == W and t.stride(1) == R * W and t.stride(0) >= 0:
+        return t
+    return t.contiguous()
+
+
+class SLGeometry:
+    """Separable mesh geometry: what model/advection.py:56-72 registers as buffers.
+
+    ``tables`` = concat(sin(lat)[H], cos(lat)[H], lon[W]) in fp32 on the compute device,
+    ``scalars`` = [min_lat, d_lat, min_lon, d_lon] (fp32 values as python floats),
+    ``windows`` = [H, W, own0, ownN, arr0, arrN, fld0, fldN] (latitude-band decomposition;
+    full mesh by default).
+    """
+
+    def __init__(self, tables: Tensor, scalars: List[float], H: int, W: int, windows=None):
+        self.tables = tables
+        self.scalars = [float(s) for s in scalars]
+        self.H, self.W = int(H), int(W)
+        self.windows = list(windows) if windows is not None else [self.H, self.W, 0, self.H, 0, self.H, 0, self.H]
+
+    @staticmethod
+    def separable(lat_grid: Tensor, lon_grid: Tensor) -> bool:
+        return bool((lat_grid == lat_grid[:, :1]).all()) and bool((lon_grid == lon_grid[:1, :]).all())
+
+    @classmethod
+    def from_grids(cls, lat_grid: Tensor, lon_grid: Tensor) -> "SLGeometry":
+        """lat_grid, lon_grid: [H, W] radians, as data/era5_dataset.py:178-182 builds them.
+        sin/cos are taken with torch on the device the grids live on, i.e. the same fp32
+        kernels the reference applies to its ``lat_grid`` buffer (advection.py:86-87)."""
+        if lat_grid.dim() != 2 or lat_grid.shape != lon_grid.shape:
+            raise ValueError("lat_grid and lon_grid must be [H, W]")
+        if not cls.separable(lat_grid, lon_grid):
+            raise ValueError("paradis_sl needs a separable lat-lon mesh (lat constant along W, lon along H)")
+        H, W = lat_grid.shape
+        lat = lat_grid[:, 0].to(torch.float32).contiguous()
+        lon = lon_grid[0, :].to(torch.float32).contiguous()
+        tables = torch.cat([torch.sin(lat), torch.cos(lat), lon]).contiguous()
+        lat_min, lat_max = lat.min(), lat.max()
+        lon_min, lon_max = lon.min(), lon.max()
+        scalars = [lat_min.item(), (lat_max - lat_min).item(), lon_min.item(), (lon_max - lon_min).item()]
+        return cls(tables, scalars, H, W)
+
+    def to(self, device) -> "SLGeometry":
+        return SLGeometry(self.tables.to(device), self.scalars, self.H, self.W, self.windows)
+
+    def band(self, own: Tuple[int, int], arr: Tuple[int, int], fld: Tuple[int, int]) -> "SLGeometry":
+        """Same mesh, different row windows (row0, rows) for a latitude band."""
+        return SLGeometry(self.tables, self.scalars, self.H, self.W,
+                          [self.H, self.W, own[0], own[1], arr[0], arr[1], fld[0], fld[1]])
+
+
+def _geom_struct(tables: Tensor, scalars: List[float], windows: List[int]) -> _lib.Geom:
+    H, W = int(windows[0]), int(windows[1])
+    if tables.dtype != torch.float32 or tables.numel() != 2 * H + W or not tables.is_contiguous():
+        raise RuntimeError("paradis_sl: geometry tables must be a contiguous fp32 tensor of 2*H+W values")
+    base = tables.data_ptr()
+    g = _lib.Geom()
+    g.H, g.W = H, W
+    g.sin_lat, g.cos_lat, g.lon = base, base + 4 * H, base + 8 * H
+    g.min_lat, g.d_lat, g.min_lon, g.d_lon = scalars
+    g.own_row0, g.own_rows, g.arr_row0, g.arr_rows, g.fld_row0, g.fld_rows = [int(w) for w in windows[2:8]]
+    return g
+
+
+def _check_inputs(field: Tensor, u: Tensor, v: Tensor, windows: List[int]):
+    if not (field.is_cuda and u.is_cuda and v.is_cuda):
+        raise RuntimeError("paradis::sl_advect is a CUDA-only operator (no CPU fallback)")
+    if field.dim() != 4 or u.shape != v.shape or u.dim() != 4:
+        raise RuntimeError("paradis::sl_advect expects field [B,V,Rf,W] and u, v [B,V,Ra,W]")
+    H, W, own0, ownN, arr0, arrN, fld0, fldN = [int(w) for w in windows]
+    B, V = field.shape[:2]
+    if tuple(field.shape) != (B, V, fldN, W) or tuple(u.shape) != (B, V, arrN, W):
+        raise RuntimeError(f"paradis::sl_advect shape mismatch: field {tuple(field.shape)}, u {tuple(u.shape)}, "
+                           f"windows {windows}")
+    return B, V, H, W, ownN, arrN
+
+
+# --------------------------------------------------------------------------------------
+# sl_advect
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("paradis::sl_advect", mutates_args=(), device_types="cuda")
+def _sl_advect(field: Tensor, u: Tensor, v: Tensor, tables: Tensor, scalars: List[float], dt: float,
+               interp: int, pole_fix: bool, math: int, windows: List[int]) -> Tensor:
+    B, V, H, W, ownN, arrN = _check_inputs(field, u, v, windows)
+    L = _lib.lib()
+    field = _inner_contig(field.float())
+    u = _inner_contig(u.float())
+    v = _inner_contig(v.float())
+    out = torch.empty((B, V, ownN, W), dtype=torch.float32, device=field.device)
+    g = _geom_struct(tables, scalars, windows)
+    ws_bytes = L.paradis_sl_advect_fwd_workspace(B, V)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=field.device)
+    with torch.cuda.device(field.device):
+        rc = L.paradis_sl_advect_fwd(C.byref(g), _ptr(field), _ptr(u), _ptr(v), _ptr(out), B, V,
+                                     field.stride(0), u.stride(0), v.stride(0), dt, interp, int(pole_fix), math,
+                                     _ptr(ws), ws_bytes, _ptr(_status_word(field.device)), _stream(field))
+    _lib.check(rc, "paradis_sl_advect_fwd")
+    return out
+
+
+@_sl_advect.register_fake
+def _(field, u, v, tables, scalars, dt, interp, pole_fix, math, windows):
+    B, V = field.shape[:2]
+    return field.new_empty((B, V, windows[3], windows[1]), dtype=torch.float32)
+
+
+@torch.library.custom_op("paradis::sl_advect_backward", mutates_args=(), device_types="cuda")
+def _sl_advect_backward(grad_out: Tensor, field: Tensor, u: Tensor, v: Tensor, tables: Tensor,
+                        scalars: List[float], dt: float, interp: int, pole_fix: bool, math: int,
+                        windows: List[int], need_field: bool, need_uv: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    B, V, H, W, ownN, arrN = _check_inputs(field, u, v, windows)
+    L = _lib.lib()
+    dev = field.device
+    field = _inner_contig(field.float())
+    u = _inner_contig(u.float())
+    v = _inner_contig(v.float())
+    grad_out = _inner_contig(grad_out.float())
+    if tuple(grad_out.shape) != (B, V, arrN, W):
+        raise RuntimeError("paradis::sl_advect_backward: grad_out must cover the arrival window")
+    gf = torch.empty((B, V, ownN, W), dtype=torch.float32, device=dev) if need_field else None
+    gu = torch.empty((B, V, ownN, W), dtype=torch.float32, device=dev) if need_uv else None
+    gv = torch.empty((B, V, ownN, W), dtype=torch.float32, device=dev) if need_uv else None
+    g = _geom_struct(tables, scalars, windows)
+    ws_bytes = L.paradis_sl_advect_bwd_workspace(B, V, arrN, W)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.paradis_sl_advect_bwd(C.byref(g), _ptr(grad_out), _ptr(field), _ptr(u), _ptr(v), _ptr(gf), _ptr(gu),
+                                     _ptr(gv), B, V, grad_out.stride(0), field.stride(0), u.stride(0), v.stride(0),
+                                     dt, interp, int(pole_fix), math, _ptr(ws), ws_bytes,
+                                     _ptr(_status_word(dev)), _stream(field))
+    _lib.check(rc, "paradis_sl_advect_bwd")
+    none = lambda: torch.empty(0, dtype=torch.float32, device=dev)
+    return (gf if need_field else none(), gu if need_uv else none(), gv if need_uv else none())
+
+
+@_sl_advect_backward.register_fake
+def _(grad_out, field, u, v, tables, scalars, dt, interp, pole_fix, math, windows, need_field, need_uv):
+    B, V = field.shape[:2]
+    shape = (B, V, windows[3], windows[1])
+    full = lambda: field.new_empty(shape, dtype=torch.float32)
+    none = lambda: field.new_empty((0,), dtype=torch.float32)
+    return (full() if need_field else none(), full() if need_uv else none(), full() if need_uv else none())
+
+
+def _sl_setup(ctx, inputs, output):
+    field, u, v, tables, scalars, dt, interp, pole_fix, math, windows = inputs
+    ctx.save_for_backward(field, u, v, tables)
+    ctx.attrs = (scalars, dt, interp, pole_fix, math, windows)
+    ctx.dtypes = (field.dtype, u.dtype, v.dtype)
+
+
+def _sl_backward(ctx, grad_out):
+    field, u, v, tables = ctx.saved_tensors
+    scalars, dt, interp, pole_fix, math, windows = ctx.attrs
+    if list(windows[2:4]) != list(windows[4:6]):
+        raise RuntimeError("autograd through a latitude-band sl_advect needs halo'd grad_out: "
+                           "use paradis_model_b200.halo.LatBandAdvection")
+    need_field = ctx.needs_input_grad[0]
+    need_uv = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+    gf, gu, gv = torch.ops.paradis.sl_advect_backward(grad_out, field, u, v, tables, scalars, dt, interp,
+                                                      pole_fix, math, windows, need_field, need_uv)
+    gf = gf.to(ctx.dtypes[0]) if need_field else None
+    gu = gu.to(ctx.dtypes[1]) if ctx.needs_input_grad[1] else None
+    gv = gv.to(ctx.dtypes[2]) if ctx.needs_input_grad[2] else None
+    return gf, gu, gv, None, None, None, None, None, None, None
+
+
+_sl_advect.register_autograd(_sl_backward, setup_context=_sl_setup)
+
+
+def sl_advect(field: Tensor, u: Tensor, v: Tensor, geometry: SLGeometry, dt: float,
+              interpolation: str = "bilinear", pole_fix: bool = True, math: str = "fast") -> Tensor:
+    """Fused operator core: drop-in for model/advection.py:129-169.
+
+    field, u, v : [B, V, H, W] CUDA tensors (u, v may be batch-strided views).  Differentiable
+    w.r.t. all three; the backward is deterministic.  ``math="exact"`` replays the reference's
+    fp32 operation order for the departure coordinates.
+    """
+    if os.environ.get("PARADIS_SL_MATH"):
+        math = os.environ["PARADIS_SL_MATH"]
+    out = torch.ops.paradis.sl_advect(field, u, v, geometry.tables, geometry.scalars, float(dt),
+                                      _lib.INTERP[interpolation], bool(pole_fix), _lib.MATH[math],
+                                      geometry.windows)
+    if os.environ.get("PARADIS_SL_CHECK") == "1":
+        check_status(field.device)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# geocyclic_pad
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("paradis::geocyclic_pad", mutates_args=(), device_types="cuda")
+def _geocyclic_pad(x: Tensor, p: int) -> Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("paradis::geocyclic_pad is a CUDA-only operator (no CPU fallback)")
+    B, Cn, H, W = x.shape
+    xf = x.float().contiguous()
+    y = torch.empty((B, Cn, H + 2 * p, W + 2 * p), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().paradis_geocyclic_pad_fwd(_ptr(xf), _ptr(y), B * Cn, H, W, p, _stream(x))
+    _lib.check(rc, "paradis_geocyclic_pad_fwd")
+    return y.to(x.dtype)
+
+
+@_geocyclic_pad.register_fake
+def _(x, p):
+    B, Cn, H, W = x.shape
+    return x.new_empty((B, Cn, H + 2 * p, W + 2 * p))
+
+
+@torch.library.custom_op("paradis::geocyclic_pad_backward", mutates_args=(), device_types="cuda")
+def _geocyclic_pad_backward(gy: Tensor, p: int) -> Tensor:
+    B, Cn, Hp, Wp = gy.shape
+    H, W = Hp - 2 * p, Wp - 2 * p
+    gyf = gy.float().contiguous()
+    gx = torch.empty((B, Cn, H, W), dtype=torch.float32, device=gy.device)
+    with torch.cuda.device(gy.device):
+        rc = _lib.lib().paradis_geocyclic_pad_bwd(_ptr(gyf), _ptr(gx), B * Cn, H, W, p, _stream(gy))
+    _lib.check(rc, "paradis_geocyclic_pad_bwd")
+    return gx.to(gy.dtype)
+
+
+@_geocyclic_pad_backward.register_fake
+def _(gy, p):
+    B, Cn, Hp, Wp = gy.shape
+    return gy.new_empty((B, Cn, Hp - 2 * p, Wp - 2 * p))
+
+
+def _pad_setup(ctx, inputs, output):
+    ctx.p = inputs[1]
+
+
+def _pad_backward(ctx, gy):
+    return torch.ops.paradis.geocyclic_pad_backward(gy, ctx.p), None
+
+
+_geocyclic_pad.register_autograd(_pad_backward, setup_context=_pad_setup)
+
+
+def geocyclic_pad(x: Tensor, pad_width: int) -> Tensor:
+    """model/padding.py:11-39 as one kernel (identity when pad_width == 0)."""
+    if pad_width == 0:
+        return x
+    assert x.dim() == 4, "Input must be 4-dimensional [batch, channels, lat, lon]"
+    assert x.shape[3] % 2 == 0, "Number of longitude points must be even"
+    return torch.ops.paradis.geocyclic_pad(x, int(pad_width))
+
+
+# --------------------------------------------------------------------------------------
+# host-buffer entry (end-to-end measurement path)
+# --------------------------------------------------------------------------------------
+def host_fwd_bwd(geometry: SLGeometry, h_field: Tensor, h_u: Tensor, h_v: Tensor, h_grad_out: Tensor,
+                 h_out: Tensor, h_gfield: Tensor, h_gu: Tensor, h_gv: Tensor, dt: float,
+                 interpolation: str = "bilinear", pole_fix: bool = True, math: str = "fast",
+                 chunk_planes: int = 8, scratch: Tensor | None = None) -> Tensor:
+    """Forward + backward with HOST tensors (pinned recommended) through
+    ``paradis_sl_advect_fwd_bwd_host``: chunked, H2D / kernels / D2H overlapped inside the
+    library; returns (and reuses) the device scratch buffer."""
+    L = _lib.lib()
+    B, V, H, W = h_field.shape
+    for t in (h_field, h_u, h_v, h_grad_out, h_out, h_gfield, h_gu, h_gv):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != (B, V, H, W):
+            raise RuntimeError("host_fwd_bwd expects contiguous fp32 CPU tensors of one shape")
+    dev = geometry.tables.device
+    need = L.paradis_sl_host_scratch_bytes(H, W, chunk_planes)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    g = _geom_struct(geometry.tables, geometry.scalars, geometry.windows)
+    torch.cuda.current_stream(dev).synchronize()  # the library runs on its own streams
+    with torch.cuda.device(dev):
+        rc = L.paradis_sl_advect_fwd_bwd_host(C.byref(g), _ptr(h_field), _ptr(h_u), _ptr(h_v), _ptr(h_grad_out),
+                                              _ptr(h_out), _ptr(h_gfield), _ptr(h_gu), _ptr(h_gv), B * V, dt,
+                                              _lib.INTERP[interpolation], int(pole_fix), _lib.MATH[math],
+                                              chunk_planes, _ptr(scratch), scratch.numel())
+    _lib.check(rc, "paradis_sl_advect_fwd_bwd_host")
+    return scratch

@@ -1,0 +1,282 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(libparadis_sl.so via ctypes / torch.library); the oracle is only the checker."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import bad_fraction, golden_cases, load_golden, relmax
+from oracle import sl_oracle as O
+
+pytestmark = pytest.mark.gpu
+DT = 21600 * 7.29212e-5 / 8
+
+
+def P():
+    import paradis_model_b200 as pkg
+    return pkg
+
+
+def cuda_fwd_bwd(field, u, v, lat, lon, dt, go, interp, math_mode="fast", pole_fix=True):
+    pkg = P()
+    geo = pkg.SLGeometry.from_grids(lat.cuda(), lon.cuda())
+    f, uu, vv = [t.cuda().clone().requires_grad_(True) for t in (field, u, v)]
+    out = pkg.sl_advect(f, uu, vv, geo, dt, interp, pole_fix, math_mode)
+    out.backward(go.cuda())
+    pkg.check_status()
+    return out.detach().cpu(), f.grad.cpu(), uu.grad.cpu(), vv.grad.cpu()
+
+
+# ------------------------------------------------------------------ padding
+@pytest.mark.parametrize("p", [1, 2, 3])
+@pytest.mark.parametrize("hw", [(6, 8), (32, 64), (721, 1440)])
+def test_padding_bit_exact(hw, p):
+    H, W = hw
+    x = torch.arange(H * W, dtype=torch.float32).reshape(1, 1, H, W).repeat(1, 2, 1, 1)
+    x[:, 1] += 0.5
+    y = P().geocyclic_pad(x.cuda(), p).cpu()
+    assert torch.equal(y, O.geocyclic_pad(x, p))            # index map bit-exact
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_padding_backward(p):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 10, 16, generator=g)
+    gy = torch.randn(2, 3, 10 + 2 * p, 16 + 2 * p, generator=g)
+    xc = x.cuda().requires_grad_(True)
+    P().geocyclic_pad(xc, p).backward(gy.cuda())
+    assert relmax(xc.grad.cpu(), O.geocyclic_pad_adjoint(gy, p)) < 1e-6
+    gi = torch.randint(-8, 8, gy.shape, generator=g).float()      # integers: order-independent, exact
+    xc.grad = None
+    P().geocyclic_pad(xc, p).backward(gi.cuda())
+    assert torch.equal(xc.grad.cpu(), O.geocyclic_pad_adjoint(gi, p))
+
+
+def test_padding_module_asserts():
+    m = P().GeoCyclicPadding(1)
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 1, 4, 7, device="cuda"))
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 4, 8, device="cuda"))
+    x = torch.zeros(1, 1, 4, 8, device="cuda")
+    assert P().GeoCyclicPadding(0)(x) is x
+
+
+# ------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("math_mode", ["fast", "exact"])
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden(name, math_mode):
+    d = load_golden(name)
+    lat, lon = O.make_grids(d["H"], d["W"], d["poles"])
+    out, gf, gu, gv = cuda_fwd_bwd(d["field"], d["u"], d["v"], lat, lon, d["dt"], d["grad_out"],
+                                   d["interpolation"], math_mode)
+    smooth = "smooth" in name
+    assert relmax(out, d["out"]) < (1e-5 if smooth else 1e-4), "forward"
+    assert relmax(gf, d["grad_field"]) < 1e-4, "grad_field"
+    if smooth:   # north_star tolerances: fwd 1e-5, grads 1e-4 (relative to max)
+        assert relmax(gu, d["grad_u"]) < 1e-4 and relmax(gv, d["grad_v"]) < 1e-4
+    else:        # white noise: d out / d ix jumps across cell edges, allow isolated floor flips
+        assert bad_fraction(gu, d["grad_u"], 1e-4) < 2e-3 and bad_fraction(gv, d["grad_v"], 1e-4) < 2e-3
+
+
+# ------------------------------------------------------------------ oracle at model sizes
+@pytest.mark.parametrize("math_mode", ["fast", "exact"])
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+@pytest.mark.parametrize("poles,H,W", [(False, 128, 256), (True, 181, 360)])
+def test_smooth_fields_vs_oracle(poles, H, W, interp, math_mode):
+    B, V = 2, 4
+    lat, lon = O.make_grids(H, W, poles)
+    field = O.smooth_field(lat, lon, B, V).float()
+    u, v = [t.float() for t in O.smooth_velocity(lat, lon, B, V, 2.5, DT)]
+    go = O.smooth_field(lat, lon, B, V, seed=7).float()
+    ref = O.sl_advect_fwd_bwd(field, u, v, lat, lon, DT, go, interp)
+    got = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, math_mode)
+    assert relmax(got[0], ref[0]) < 1e-5
+    for a, b in zip(got[1:], ref[1:]):
+        assert relmax(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+def test_exact_mode_vs_same_device_torch(interp):
+    """White noise, against the oracle's op-order replay run by torch on the SAME GPU: the
+    departure coordinates are bit-identical, so even white noise agrees to rounding."""
+    H, W, B, V = 128, 256, 2, 8
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, False, DT)
+    dev = [t.cuda() for t in (field, u, v, lat, lon, go)]
+    ref = O.sl_advect_fwd_bwd(dev[0], dev[1], dev[2], dev[3], dev[4], DT, dev[5], interp)
+    got = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, "exact")
+    geo = O.Geometry(dev[3], dev[4])
+    assert relmax(got[0], ref[0].cpu()) < 2e-6
+    assert relmax(got[1], ref[1].cpu()) < 1e-5
+    assert bad_fraction(got[2], ref[2].cpu(), 1e-4) == 0.0
+    assert bad_fraction(got[3], ref[3].cpu(), 1e-4) == 0.0
+
+
+def test_fast_mode_white_noise_statistics():
+    """fast math vs CPU oracle on white noise: isolated floor flips only."""
+    H, W, B, V = 128, 256, 2, 8
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, False, DT)
+    ref = O.sl_advect_fwd_bwd(field, u, v, lat, lon, DT, go, "bilinear")
+    got = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, "bilinear", "fast")
+    assert bad_fraction(got[0], ref[0], 1e-4) < 1e-3
+    assert bad_fraction(got[1], ref[1], 1e-4) < 1e-3
+    assert bad_fraction(got[2], ref[2], 1e-3) < 2e-3
+
+
+# ------------------------------------------------------------------ structure
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+def test_backward_is_deterministic(interp):
+    H, W, B, V = 96, 192, 2, 6
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, True, DT, cells_sigma=3.0, cells_clip=8.0)
+    a = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp)
+    for _ in range(3):
+        b = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+
+
+def test_zero_velocity_identity():
+    H, W = 64, 128
+    lat, lon = O.make_grids(H, W, False)
+    f = torch.randn(1, 3, H, W)
+    z = torch.zeros(1, 3, H, W)
+    geo = P().SLGeometry.from_grids(lat.cuda(), lon.cuda())
+    out = P().sl_advect(f.cuda(), z.cuda(), z.cuda(), geo, DT, "bilinear").cpu()
+    assert relmax(out, O.pole_mean(f)) < 2e-5
+
+
+def test_strided_velocity_views_and_no_pole_fix():
+    """u, v as views of one [B, 2V, H, W] tensor (model/paradis.py:235-237)."""
+    H, W, B, V = 48, 96, 3, 5
+    lat, lon = O.make_grids(H, W, True)
+    g = torch.Generator().manual_seed(2)
+    vel = (torch.randn(B, 2 * V, H, W, generator=g) * 0.05).cuda()
+    velv = vel.view(B, 2, V, H, W)
+    u, v = velv[:, 0], velv[:, 1]
+    assert not u.is_contiguous()
+    field = torch.randn(B, V, H, W, generator=g)
+    geo = P().SLGeometry.from_grids(lat.cuda(), lon.cuda())
+    for pole_fix in (True, False):
+        out = P().sl_advect(field.cuda(), u, v, geo, DT, "bilinear", pole_fix).cpu()
+        ref = O.sl_advect(field, u.cpu().contiguous(), v.cpu().contiguous(), lat, lon, DT, "bilinear", pole_fix)
+        assert bad_fraction(out, ref, 1e-4) < 1e-3
+
+
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+def test_adjoint_identity_full_size(interp):
+    """Size-independent property at the BASELINE size (721x1440): the operator is linear in
+    `field`, so <A f, g> == <f, A^T g>.  Checks grad_field (inverse-stencil gather, pole folds,
+    longitude wrap) against the forward kernel without any oracle."""
+    H, W, B, V = 721, 1440, 1, 8
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, True, DT)
+    pkg = P()
+    geo = pkg.SLGeometry.from_grids(lat.cuda(), lon.cuda())
+    f = field.cuda().requires_grad_(True)
+    out = pkg.sl_advect(f, u.cuda(), v.cuda(), geo, DT, interp)
+    out.backward(go.cuda())
+    lhs = (out.detach().double() * go.cuda().double()).sum()
+    rhs = (f.grad.double() * field.cuda().double()).sum()
+    pkg.check_status()
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-5
+    # linearity: A(2f + h) == 2 A f + A h
+    h = torch.randn_like(field).cuda()
+    o2 = pkg.sl_advect(2 * field.cuda() + h, u.cuda(), v.cuda(), geo, DT, interp)
+    o3 = pkg.sl_advect(h, u.cuda(), v.cuda(), geo, DT, interp)
+    assert relmax((2 * out.detach() + o3).cpu(), o2.cpu()) < 1e-5
+
+
+def test_large_displacement_window():
+    """Displacements of ~20 rows: the gather window follows the measured reach."""
+    H, W, B, V = 91, 180, 1, 3
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, True, DT, cells_sigma=8.0, cells_clip=24.0)
+    ref = O.sl_advect_fwd_bwd(field, u, v, lat, lon, DT, go, "bilinear")
+    got = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, "bilinear", "fast")
+    assert bad_fraction(got[0], ref[0], 1e-4) < 2e-3
+    assert bad_fraction(got[1], ref[1], 1e-4) < 2e-3
+
+
+def test_lat_band_windows_are_bit_identical():
+    """Two latitude bands with halos reproduce the single-call result bit for bit."""
+    H, W, B, V = 64, 128, 1, 4
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, True, DT, cells_sigma=1.0, cells_clip=2.0)
+    pkg = P()
+    geo = pkg.SLGeometry.from_grids(lat.cuda(), lon.cuda())
+    fc, uc, vc, gc = [t.cuda() for t in (field, u, v, go)]
+    full = torch.ops.paradis.sl_advect(fc, uc, vc, geo.tables, geo.scalars, DT, 1, True, 0, geo.windows)
+    gfull = torch.ops.paradis.sl_advect_backward(gc, fc, uc, vc, geo.tables, geo.scalars, DT, 1, True, 0,
+                                                 geo.windows, True, True)
+    halo = 6
+    outs, gfs, gus = [], [], []
+    for (r0, n) in [(0, 32), (32, 32)]:
+        f0, f1 = max(0, r0 - halo), min(H, r0 + n + halo)
+        gb = geo.band((r0, n), (r0, n), (f0, f1 - f0))
+        outs.append(torch.ops.paradis.sl_advect(fc[:, :, f0:f1].contiguous(), uc[:, :, r0:r0 + n].contiguous(),
+                                                vc[:, :, r0:r0 + n].contiguous(), gb.tables, gb.scalars, DT, 1,
+                                                True, 0, gb.windows))
+        gb2 = geo.band((r0, n), (f0, f1 - f0), (f0, f1 - f0))
+        r = torch.ops.paradis.sl_advect_backward(gc[:, :, f0:f1].contiguous(), fc[:, :, f0:f1].contiguous(),
+                                                 uc[:, :, f0:f1].contiguous(), vc[:, :, f0:f1].contiguous(),
+                                                 gb2.tables, gb2.scalars, DT, 1, True, 0, gb2.windows, True, True)
+        gfs.append(r[0]); gus.append(r[1])
+    pkg.check_status()
+    assert torch.equal(torch.cat(outs, 2), full)
+    assert torch.equal(torch.cat(gfs, 2), gfull[0])
+    assert torch.equal(torch.cat(gus, 2), gfull[1])
+
+
+def test_halo_violation_is_reported():
+    H, W = 64, 128
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, 1, 1, True, DT, cells_sigma=4.0, cells_clip=8.0)
+    pkg = P()
+    geo = pkg.SLGeometry.from_grids(lat.cuda(), lon.cuda()).band((20, 10), (20, 10), (19, 12))
+    torch.ops.paradis.sl_advect(field[:, :, 19:31].contiguous().cuda(), u[:, :, 20:30].contiguous().cuda(),
+                                v[:, :, 20:30].contiguous().cuda(), geo.tables, geo.scalars, DT, 1, True, 0,
+                                geo.windows)
+    with pytest.raises(RuntimeError, match="DISPLACEMENT"):
+        pkg.check_status()
+
+
+def test_host_entry_matches_device_path():
+    H, W, B, V = 64, 128, 2, 5
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, False, DT)
+    pkg = P()
+    geo = pkg.SLGeometry.from_grids(lat.cuda(), lon.cuda())
+    dev = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, "bilinear")
+    pin = lambda t: t.contiguous().pin_memory()
+    hin = [pin(t) for t in (field, u, v, go)]
+    hout = [pin(torch.empty_like(field)) for _ in range(4)]
+    pkg.host_fwd_bwd(geo, *hin, *hout, DT, "bilinear", True, "fast", chunk_planes=3)
+    for a, b in zip(hout, dev):
+        assert torch.equal(a, b)
+
+
+def test_module_drop_in_autograd_and_state_dict():
+    """NeuralSemiLagrangian keeps the reference's parameter names and differentiates end to end."""
+    pkg = P()
+
+    class NS(dict):
+        __getattr__ = dict.__getitem__
+
+    cfg = NS(model=NS(physblock=NS(advection=NS(down_projection=NS(layers=["SepConv"], hidden_dim=0),
+                                                up_projection=NS(layers=["CLinear"], hidden_dim=0)))))
+    H, W, hidden, V, B = 32, 64, 12, 6, 2
+    lat, lon = O.make_grids(H, W, True)
+    torch.manual_seed(0)
+    m = pkg.NeuralSemiLagrangian(cfg, hidden, (H, W), V, lat, lon, "bilinear").cuda()
+    assert sorted(m.state_dict()) == ["down_projection.0-SepConv.depthwise.weight",
+                                      "down_projection.0-SepConv.pointwise.bias",
+                                      "down_projection.0-SepConv.pointwise.weight",
+                                      "up_projection.0-CLinear.conv.bias", "up_projection.0-CLinear.conv.weight"]
+    hid = torch.randn(B, hidden, H, W, device="cuda", requires_grad=True)
+    vel = (torch.randn(B, 2 * V, H, W, device="cuda") * 0.05).requires_grad_(True)
+    velv = vel.view(B, 2, V, H, W)
+    out = m(hid, velv[:, 0], velv[:, 1], DT)
+    out.square().mean().backward()
+    assert out.shape == (B, hidden, H, W)
+    assert hid.grad is not None and vel.grad is not None and torch.isfinite(vel.grad).all()
+    # same computation with the oracle core in place of the fused op
+    proj = m.down_projection(hid.detach()).cpu()
+    core = O.sl_advect(proj, velv[:, 0].detach().cpu(), velv[:, 1].detach().cpu(), lat, lon, DT, "bilinear")
+    ref = m.up_projection(core.cuda())
+    assert relmax(out.detach().cpu(), ref.detach().cpu()) < 1e-4
