@@ -112,14 +112,20 @@ int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* field, const
  * (no atomics).
  *   grad_out, u, v [B, V, arr_rows, W]; field [B, V, fld_rows, W];
  *   grad_field, grad_u, grad_v [B, V, own_rows, W] contiguous.
- * grad_field may be NULL (skips the adjoint gather); grad_u and grad_v may both be NULL. */
+ * grad_field may be NULL (skips the adjoint gather); grad_u and grad_v may both be NULL.
+ * `phases` selects the kernels to enqueue: PARADIS_BWD_ARRIVAL (grad_u, grad_v and the row
+ * classes of every arrival point, kept in the workspace), PARADIS_BWD_GATHER (grad_field
+ * from the classes left in the SAME workspace by an earlier ARRIVAL call), or both. */
+#define PARADIS_BWD_ARRIVAL 1
+#define PARADIS_BWD_GATHER 2
+#define PARADIS_BWD_ALL 3
 size_t paradis_sl_advect_bwd_workspace(int B, int V, int arr_rows, int W);
 int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* grad_out,
                           const float* field, const float* u, const float* v, float* grad_field,
                           float* grad_u, float* grad_v, int B, int V, int64_t gout_sB,
                           int64_t field_sB, int64_t u_sB, int64_t v_sB, float dt, int interp,
-                          int pole_fix, int math, void* workspace, size_t workspace_bytes,
-                          int32_t* status, void* stream);
+                          int pole_fix, int math, int phases, void* workspace,
+                          size_t workspace_bytes, int32_t* status, void* stream);
 
 /* ---- Host-buffer entry (end-to-end path) --------------------------------------------
  * Same operator (single GPU, full mesh) with HOST pointers (pinned memory recommended):

@@ -9,7 +9,7 @@ CUDA operator, ``torch.ops.paradis.sl_advect``.
 """
 import torch
 
-from .ops import SLGeometry, sl_advect
+from .ops import SLGeometry, pack_tables, sl_advect
 from .padding import GeoCyclicPadding
 from .projection import resolve_block_factory
 
@@ -66,7 +66,7 @@ class NeuralSemiLagrangian(torch.nn.Module):
         # exactly what the reference evaluates per call (advection.py:86-87)
         lat = self.lat_grid[0, 0, :, 0].float()
         lon = self.lon_grid[0, 0, 0, :].float()
-        self.sl_tables = torch.cat([torch.sin(lat), torch.cos(lat), lon]).contiguous()
+        self.sl_tables = pack_tables(lat, lon)
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)

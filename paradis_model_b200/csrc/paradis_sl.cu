@@ -54,6 +54,10 @@ __device__ __forceinline__ const float* plane_ptr(const float* base, long long s
   const int b = pl / V, c = pl - b * V;
   return base + (long long)b * sB + (long long)c * rows * W;
 }
+// same, for kernels launched on a (blocks, V, B) grid: no integer division
+__device__ __forceinline__ const float* plane_ptr_bc(const float* base, long long sB, int b, int c, int rows, int W) {
+  return base + (long long)b * sB + (long long)c * rows * W;
+}
 
 // deterministic zonal sum of one row by one warp (fixed lane/iteration order)
 __device__ __forceinline__ float warp_row_sum(const float* row, int W, int lane) {
@@ -95,51 +99,19 @@ __global__ void pole_rows_fix_kernel(float* __restrict__ t, int rows, int row0, 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int INTERP>
-__device__ __forceinline__ float sample(const Params& P, const float* __restrict__ f, const Traj& t,
-                                        float mean0, float mean1) {
-  constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
-  const float fx = floorf(t.ix), fy = floorf(t.iy);
-  const float tx = __fsub_rn(t.ix, fx), ty = __fsub_rn(t.iy, fy);
-  const int x0 = (int)fx + OMIN, y0 = (int)fy + OMIN;
-  float wx[NT], wy[NT], d0[NT], d1[NT];
-  axis_weights<INTERP, false>(tx, wx, d0);
-  axis_weights<INTERP, false>(ty, wy, d1);
-  float acc = 0.0f;
-  if (INTERP == 1) {
-    // ATen bilinear order: nw, ne, sw, se, weights formed first, FMA accumulate
-    const float v00 = tap_value(P, f, y0, x0, mean0, mean1), v01 = tap_value(P, f, y0, x0 + 1, mean0, mean1);
-    const float v10 = tap_value(P, f, y0 + 1, x0, mean0, mean1), v11 = tap_value(P, f, y0 + 1, x0 + 1, mean0, mean1);
-    acc = __fmul_rn(v00, __fmul_rn(wx[0], wy[0]));
-    acc = __fmaf_rn(v01, __fmul_rn(wx[1], wy[0]), acc);
-    acc = __fmaf_rn(v10, __fmul_rn(wx[0], wy[1]), acc);
-    acc = __fmaf_rn(v11, __fmul_rn(wx[1], wy[1]), acc);
-  } else {
-    // ATen bicubic: interpolate each row along x, then along y
-#pragma unroll
-    for (int a = 0; a < NT; ++a) {
-      float r = 0.0f;
-#pragma unroll
-      for (int b = 0; b < NT; ++b) r = __fmaf_rn(tap_value(P, f, y0 + a, x0 + b, mean0, mean1), wx[b], r);
-      acc = __fmaf_rn(r, wy[a], acc);
-    }
-  }
-  return acc;
-}
-
 template <bool EXACT, int INTERP, int VEC>
 __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
-  const int pl = blockIdx.y;
+  const int c = blockIdx.y, b = blockIdx.z, pl = b * P.V + c;
   const unsigned unit = blockIdx.x * blockDim.x + threadIdx.x;
   if (unit >= (unsigned)(P.ownN * P.upr)) return;
   const unsigned r = P.w4_mul ? fast_div(unit, P.w4_mul, P.w4_shift) : unit / (unsigned)P.upr;
   const int x = (unit - r * P.upr) * VEC;
   const int y = P.own0 + (int)r;  // global arrival row
   const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
-  const float* f = plane_ptr(P.field, P.field_sB, P.V, P.fldN, P.W, pl);
-  const long long aoff = (long long)(y - P.arr0) * P.W + x;
-  const float* up = plane_ptr(P.u, P.u_sB, P.V, P.arrN, P.W, pl) + aoff;
-  const float* vp = plane_ptr(P.v, P.v_sB, P.V, P.arrN, P.W, pl) + aoff;
+  const float* f = plane_ptr_bc(P.field, P.field_sB, b, c, P.fldN, P.W);
+  const int aoff = (y - P.arr0) * P.W + x;
+  const float* up = plane_ptr_bc(P.u, P.u_sB, b, c, P.arrN, P.W) + aoff;
+  const float* vp = plane_ptr_bc(P.v, P.v_sB, b, c, P.arrN, P.W) + aoff;
   float mean0 = 0.0f, mean1 = 0.0f;
   if (P.pole_fix) { mean0 = __ldg(P.fmean + 2 * pl); mean1 = __ldg(P.fmean + 2 * pl + 1); }
   float uu[VEC], vv[VEC], ll[VEC], oo[VEC];
@@ -155,7 +127,8 @@ __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
   for (int k = 0; k < VEC; ++k) {
     Traj t;
     trajectory<EXACT>(P, uu[k], vv[k], sp, cp, ll[k], t);
-    oo[k] = sample<INTERP>(P, f, t, mean0, mean1);
+    float dx, dy;
+    stencil_eval<INTERP, false>(P, f, t, mean0, mean1, oo[k], dx, dy);
   }
   float* op = P.out + ((long long)pl * P.ownN + r) * P.W + x;
   if (VEC == 4) __stcs(reinterpret_cast<float4*>(op), *reinterpret_cast<float4*>(oo));
@@ -168,31 +141,6 @@ __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
 // ---------------------------------------------------------------------------------------------
 // backward, per arrival point: grad_u, grad_v and the row class of the departure cell
 // ---------------------------------------------------------------------------------------------
-template <int INTERP>
-__device__ __forceinline__ void sample_grad(const Params& P, const float* __restrict__ f, const Traj& t,
-                                            float mean0, float mean1, float& dx, float& dy) {
-  constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
-  const float fx = floorf(t.ix), fy = floorf(t.iy);
-  const float tx = __fsub_rn(t.ix, fx), ty = __fsub_rn(t.iy, fy);
-  const int x0 = (int)fx + OMIN, y0 = (int)fy + OMIN;
-  float wx[NT], wy[NT], dwx[NT], dwy[NT];
-  axis_weights<INTERP, true>(tx, wx, dwx);
-  axis_weights<INTERP, true>(ty, wy, dwy);
-  dx = 0.0f; dy = 0.0f;
-#pragma unroll
-  for (int a = 0; a < NT; ++a) {
-    float r = 0.0f, rd = 0.0f;
-#pragma unroll
-    for (int b = 0; b < NT; ++b) {
-      const float val = tap_value(P, f, y0 + a, x0 + b, mean0, mean1);
-      r = fmaf(val, wx[b], r);
-      rd = fmaf(val, dwx[b], rd);
-    }
-    dx = fmaf(rd, wy[a], dx);
-    dy = fmaf(r, dwy[a], dy);
-  }
-}
-
 // Jacobian of (ix, iy) w.r.t. (u, v): closed form of SURVEY 8a, validated in oracle/sl_oracle.py
 __device__ __forceinline__ void velocity_grads(const Params& P, const Traj& t, float sp, float cp, float gix,
                                                float giy, float& gu, float& gv) {
@@ -213,7 +161,7 @@ __device__ __forceinline__ void velocity_grads(const Params& P, const Traj& t, f
 
 template <bool EXACT, int INTERP, int VEC>
 __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
-  const int pl = blockIdx.y;
+  const int c = blockIdx.y, b = blockIdx.z, pl = b * P.V + c;
   const unsigned unit = blockIdx.x * blockDim.x + threadIdx.x;
   int reach = 0;
   if (unit < (unsigned)(P.arrN * P.upr)) {
@@ -222,9 +170,9 @@ __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
     const int y = P.arr0 + (int)r;  // global arrival row
     const bool own = (y >= P.own0) && (y < P.own0 + P.ownN) && (P.gu != nullptr);
     const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
-    const long long aoff = (long long)r * P.W + x;
-    const float* up = plane_ptr(P.u, P.u_sB, P.V, P.arrN, P.W, pl) + aoff;
-    const float* vp = plane_ptr(P.v, P.v_sB, P.V, P.arrN, P.W, pl) + aoff;
+    const int aoff = (int)r * P.W + x;
+    const float* up = plane_ptr_bc(P.u, P.u_sB, b, c, P.arrN, P.W) + aoff;
+    const float* vp = plane_ptr_bc(P.v, P.v_sB, b, c, P.arrN, P.W) + aoff;
     float uu[VEC], vv[VEC], ll[VEC], gg[VEC], ou[VEC], ov[VEC];
     signed char cc[VEC];
     if (VEC == 4) {
@@ -238,8 +186,8 @@ __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
     const float* f = nullptr;
     float mean0 = 0.0f, mean1 = 0.0f;
     if (own) {
-      f = plane_ptr(P.field, P.field_sB, P.V, P.fldN, P.W, pl);
-      const float* gp = plane_ptr(P.gout, P.gout_sB, P.V, P.arrN, P.W, pl) + aoff;
+      f = plane_ptr_bc(P.field, P.field_sB, b, c, P.fldN, P.W);
+      const float* gp = plane_ptr_bc(P.gout, P.gout_sB, b, c, P.arrN, P.W) + aoff;
       if (VEC == 4) *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(gp));
       else {
 #pragma unroll
@@ -258,17 +206,17 @@ __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
     for (int k = 0; k < VEC; ++k) {
       Traj t;
       trajectory<EXACT>(P, uu[k], vv[k], sp, cp, ll[k], t);
-      int c = (int)floorf(t.iy) - (y + P.p);
-      const int ac = abs(c);
+      int rc = (int)floorf(t.iy) - (y + P.p);
+      const int ac = abs(rc);
       if (ac > PARADIS_SL_MAX_DISP_ROWS) {
         if (P.status) *P.status = PARADIS_ERR_DISPLACEMENT;
-        c = c > 0 ? 127 : -127;
+        rc = rc > 0 ? 127 : -127;
       }
       reach = max(reach, min(ac, 127));
-      cc[k] = (signed char)c;
+      cc[k] = (signed char)rc;
       if (own) {
-        float dx, dy;
-        sample_grad<INTERP>(P, f, t, mean0, mean1, dx, dy);
+        float val, dx, dy;
+        stencil_eval<INTERP, true>(P, f, t, mean0, mean1, val, dx, dy);
         velocity_grads(P, t, sp, cp, gg[k] * dx, gg[k] * dy, ou[k], ov[k]);
       }
     }
@@ -562,6 +510,14 @@ static int fill_params(Params& P, const paradis_sl_geom* g, int B, int V, float 
   P.Cy = (float)((double)p - (double)g->min_lat * (double)P.Ay);
   P.clamp_lo = (float)(-1 + 1e-7); P.clamp_hi = (float)(1 - 1e-7);
   P.B = B; P.V = V; P.pole_fix = pole_fix ? 1 : 0;
+  {  // rows (global, of tap row 0) whose whole stencil is plain field data inside the window
+    const int nt = interp == 1 ? 2 : 4;
+    const int lo = P.fld0 > (pole_fix ? 1 : 0) ? P.fld0 : (pole_fix ? 1 : 0);
+    const int top = (P.fld0 + P.fldN - 1) < (pole_fix ? P.H - 2 : P.H - 1) ? (P.fld0 + P.fldN - 1) : (pole_fix ? P.H - 2 : P.H - 1);
+    const int hi = top - (nt - 1);
+    if (hi >= lo && P.W >= nt) { P.fast_y0 = lo; P.fast_yspan = hi - lo; }
+    else { P.fast_y0 = 1 << 30; P.fast_yspan = 0; }
+  }
   return PARADIS_OK;
 }
 
@@ -610,7 +566,7 @@ extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* f
   const int vec = vec_ok ? 4 : 1;
   set_units(P, vec, P.ownN);
   const unsigned units = (unsigned)P.ownN * P.upr;
-  dim3 grid((units + 255) / 256, planes);
+  dim3 grid((units + 255) / 256, V, B);
   const bool exact = math == PARADIS_MATH_EXACT;
   if (interp == 1) { if (exact) launch_fwd<true, 1>(P, vec, grid, st); else launch_fwd<false, 1>(P, vec, grid, st); }
   else             { if (exact) launch_fwd<true, 2>(P, vec, grid, st); else launch_fwd<false, 2>(P, vec, grid, st); }
@@ -643,17 +599,20 @@ extern "C" size_t paradis_sl_advect_bwd_workspace(int B, int V, int arr_rows, in
 }
 
 template <bool EXACT, int INTERP>
-static int launch_bwd(Params& P, int vec, cudaStream_t st, bool want_field) {
+static int launch_bwd(Params& P, int vec, cudaStream_t st, bool want_field, int phases) {
   const int planes = P.B * P.V;
   set_units(P, vec, P.arrN);
   const unsigned units = (unsigned)P.arrN * P.upr;
-  dim3 grid((units + 255) / 256, planes);
+  dim3 grid((units + 255) / 256, P.V, P.B);
   if ((int)grid.x > P.nblk) return fail(PARADIS_ERR_WORKSPACE, "internal: blkmax layout");
   P.nblk = grid.x;
-  if (vec == 4) sl_bwd_arrival_kernel<EXACT, INTERP, 4><<<grid, 256, 0, st>>>(P);
-  else sl_bwd_arrival_kernel<EXACT, INTERP, 1><<<grid, 256, 0, st>>>(P);
-  if (!want_field) return PARADIS_OK;
-  plane_reach_kernel<<<(planes * 32 + 255) / 256, 256, 0, st>>>(P.blkmax, P.nblk, planes, P.plane_reach);
+  if (phases & PARADIS_BWD_ARRIVAL) {
+    if (vec == 4) sl_bwd_arrival_kernel<EXACT, INTERP, 4><<<grid, 256, 0, st>>>(P);
+    else sl_bwd_arrival_kernel<EXACT, INTERP, 1><<<grid, 256, 0, st>>>(P);
+    if (want_field)
+      plane_reach_kernel<<<(planes * 32 + 255) / 256, 256, 0, st>>>(P.blkmax, P.nblk, planes, P.plane_reach);
+  }
+  if (!want_field || !(phases & PARADIS_BWD_GATHER)) return PARADIS_OK;
   const size_t smem = (size_t)kGatherWarps * (P.W + kQueue) * sizeof(float);
   if (smem > 227 * 1024) return fail(PARADIS_ERR_BAD_SHAPE, "W=%d too wide for the gather kernel's shared memory", P.W);
   auto kern = sl_bwd_gather_kernel<EXACT, INTERP>;
@@ -667,11 +626,12 @@ static int launch_bwd(Params& P, int vec, cudaStream_t st, bool want_field) {
 extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* grad_out, const float* field,
                                      const float* u, const float* v, float* grad_field, float* grad_u,
                                      float* grad_v, int B, int V, int64_t gout_sB, int64_t field_sB, int64_t u_sB,
-                                     int64_t v_sB, float dt, int interp, int pole_fix, int math, void* workspace,
-                                     size_t workspace_bytes, int32_t* status, void* stream) {
+                                     int64_t v_sB, float dt, int interp, int pole_fix, int math, int phases,
+                                     void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
   Params P;
   if (int rc = fill_params(P, geom, B, V, dt, interp, pole_fix)) return rc;
   if (!grad_out || !field || !u || !v) return fail(PARADIS_ERR_NULL_POINTER, "NULL tensor pointer");
+  if (phases < 1 || phases > 3) return fail(PARADIS_ERR_BAD_SHAPE, "phases must be 1, 2 or 3");
   if ((grad_u == nullptr) != (grad_v == nullptr)) return fail(PARADIS_ERR_NULL_POINTER, "grad_u and grad_v must both be given or both be NULL");
   const BwdWs L = bwd_layout(B, V, P.arrN, P.W);
   if (!workspace || workspace_bytes < L.total)
@@ -690,7 +650,7 @@ extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* g
   P.blkmax = grad_field ? (unsigned char*)(ws + L.blkmax) : nullptr;
   P.cls = grad_field ? (signed char*)(ws + L.cls) : nullptr;
   P.nblk = L.nblk;
-  if (pole_fix) {
+  if (pole_fix && (phases & PARADIS_BWD_ARRIVAL)) {
     const int warps = planes * 2;
     pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(field, field_sB, V, P.fldN, P.fld0, P.H, P.W, planes, fmean);
     pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(grad_out, gout_sB, V, P.arrN, P.arr0, P.H, P.W, planes, gmean);
@@ -701,8 +661,9 @@ extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* g
   const int vec = vec_ok ? 4 : 1;
   const bool exact = math == PARADIS_MATH_EXACT;
   int rc;
-  if (interp == 1) rc = exact ? launch_bwd<true, 1>(P, vec, st, grad_field != nullptr) : launch_bwd<false, 1>(P, vec, st, grad_field != nullptr);
-  else             rc = exact ? launch_bwd<true, 2>(P, vec, st, grad_field != nullptr) : launch_bwd<false, 2>(P, vec, st, grad_field != nullptr);
+  const bool wf = grad_field != nullptr;
+  if (interp == 1) rc = exact ? launch_bwd<true, 1>(P, vec, st, wf, phases) : launch_bwd<false, 1>(P, vec, st, wf, phases);
+  else             rc = exact ? launch_bwd<true, 2>(P, vec, st, wf, phases) : launch_bwd<false, 2>(P, vec, st, wf, phases);
   if (rc) return rc;
   return check_launch("paradis_sl_advect_bwd");
 }
@@ -800,7 +761,7 @@ extern "C" int paradis_sl_advect_fwd_bwd_host(const paradis_sl_geom* geom, const
     if (rc) break;
     cudaMemcpyAsync(h_out + off, dout, bytes, cudaMemcpyDeviceToHost, s);
     rc = paradis_sl_advect_bwd(geom, dg, df, du, dv, dgf, dgu, dgv, 1, c, sB, sB, sB, sB, dt, interp, pole_fix, math,
-                               base + L.wsb, paradis_sl_advect_bwd_workspace(1, c, H, W), nullptr, s);
+                               PARADIS_BWD_ALL, base + L.wsb, paradis_sl_advect_bwd_workspace(1, c, H, W), nullptr, s);
     if (rc) break;
     cudaMemcpyAsync(h_grad_field + off, dgf, bytes, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(h_grad_u + off, dgu, bytes, cudaMemcpyDeviceToHost, s);

@@ -62,10 +62,27 @@ def _inner_contig(t: Tensor) -> Tensor:
     return t.contiguous()
 
 
+def _hpad(H: int) -> int:
+    return (H + 3) // 4 * 4
+
+
+def pack_tables(lat: Tensor, lon: Tensor) -> Tensor:
+    """[sin(lat) | cos(lat) | lon], fp32, latitude sections zero-padded to 4-entry multiples.
+    sin/cos run as torch fp32 kernels on the device of ``lat`` (what the reference evaluates
+    on its ``lat_grid`` buffer, advection.py:86-87)."""
+    H, Hp = lat.numel(), _hpad(lat.numel())
+    t = torch.zeros(2 * Hp + lon.numel(), dtype=torch.float32, device=lat.device)
+    t[:H] = torch.sin(lat.float())
+    t[Hp:Hp + H] = torch.cos(lat.float())
+    t[2 * Hp:] = lon.float()
+    return t
+
+
 class SLGeometry:
     """Separable mesh geometry: what model/advection.py:56-72 registers as buffers.
 
-    ``tables`` = concat(sin(lat)[H], cos(lat)[H], lon[W]) in fp32 on the compute device,
+    ``tables`` = [sin(lat) | cos(lat) | lon] in fp32 on the compute device, the two latitude
+    sections padded to a multiple of 4 entries so every section is 16-byte aligned,
     ``scalars`` = [min_lat, d_lat, min_lon, d_lon] (fp32 values as python floats),
     ``windows`` = [H, W, own0, ownN, arr0, arrN, fld0, fldN] (latitude-band decomposition;
     full mesh by default).
@@ -93,7 +110,7 @@ class SLGeometry:
         H, W = lat_grid.shape
         lat = lat_grid[:, 0].to(torch.float32).contiguous()
         lon = lon_grid[0, :].to(torch.float32).contiguous()
-        tables = torch.cat([torch.sin(lat), torch.cos(lat), lon]).contiguous()
+        tables = pack_tables(lat, lon)
         lat_min, lat_max = lat.min(), lat.max()
         lon_min, lon_max = lon.min(), lon.max()
         scalars = [lat_min.item(), (lat_max - lat_min).item(), lon_min.item(), (lon_max - lon_min).item()]
@@ -110,12 +127,13 @@ class SLGeometry:
 
 def _geom_struct(tables: Tensor, scalars: List[float], windows: List[int]) -> _lib.Geom:
     H, W = int(windows[0]), int(windows[1])
-    if tables.dtype != torch.float32 or tables.numel() != 2 * H + W or not tables.is_contiguous():
-        raise RuntimeError("paradis_sl: geometry tables must be a contiguous fp32 tensor of 2*H+W values")
+    Hp = _hpad(H)
+    if tables.dtype != torch.float32 or tables.numel() != 2 * Hp + W or not tables.is_contiguous():
+        raise RuntimeError("paradis_sl: geometry tables must be a contiguous fp32 tensor from pack_tables()")
     base = tables.data_ptr()
     g = _lib.Geom()
     g.H, g.W = H, W
-    g.sin_lat, g.cos_lat, g.lon = base, base + 4 * H, base + 8 * H
+    g.sin_lat, g.cos_lat, g.lon = base, base + 4 * Hp, base + 8 * Hp
     g.min_lat, g.d_lat, g.min_lon, g.d_lon = scalars
     g.own_row0, g.own_rows, g.arr_row0, g.arr_rows, g.fld_row0, g.fld_rows = [int(w) for w in windows[2:8]]
     return g
@@ -185,7 +203,7 @@ def _sl_advect_backward(grad_out: Tensor, field: Tensor, u: Tensor, v: Tensor, t
     with torch.cuda.device(dev):
         rc = L.paradis_sl_advect_bwd(C.byref(g), _ptr(grad_out), _ptr(field), _ptr(u), _ptr(v), _ptr(gf), _ptr(gu),
                                      _ptr(gv), B, V, grad_out.stride(0), field.stride(0), u.stride(0), v.stride(0),
-                                     dt, interp, int(pole_fix), math, _ptr(ws), ws_bytes,
+                                     dt, interp, int(pole_fix), math, 3, _ptr(ws), ws_bytes,
                                      _ptr(_status_word(dev)), _stream(field))
     _lib.check(rc, "paradis_sl_advect_bwd")
     none = lambda: torch.empty(0, dtype=torch.float32, device=dev)
@@ -333,3 +351,41 @@ def host_fwd_bwd(geometry: SLGeometry, h_field: Tensor, h_u: Tensor, h_v: Tensor
                                               chunk_planes, _ptr(scratch), scratch.numel())
     _lib.check(rc, "paradis_sl_advect_fwd_bwd_host")
     return scratch
+
+
+# --------------------------------------------------------------------------------------
+# low-level access for measurement: backward phases separately, caller-held buffers
+# --------------------------------------------------------------------------------------
+class RawAdvection:
+    """Pre-allocated buffers + direct C-ABI calls (no autograd, no allocation per call).
+    Used by bench.py to time forward, backward-arrival and backward-gather separately."""
+
+    def __init__(self, geometry: SLGeometry, B: int, V: int, interpolation="bilinear", pole_fix=True, math="fast"):
+        self.geo, self.B, self.V = geometry, B, V
+        self.interp, self.pole_fix, self.math = _lib.INTERP[interpolation], int(pole_fix), _lib.MATH[math]
+        dev = geometry.tables.device
+        L = _lib.lib()
+        H, W, own0, ownN, arr0, arrN, fld0, fldN = geometry.windows
+        self.out = torch.empty((B, V, ownN, W), dtype=torch.float32, device=dev)
+        self.gfield, self.gu, self.gv = [torch.empty_like(self.out) for _ in range(3)]
+        self.ws_f = torch.empty(L.paradis_sl_advect_fwd_workspace(B, V), dtype=torch.uint8, device=dev)
+        self.ws_b = torch.empty(L.paradis_sl_advect_bwd_workspace(B, V, arrN, W), dtype=torch.uint8, device=dev)
+        self.g = _geom_struct(geometry.tables, geometry.scalars, geometry.windows)
+        self.status = _status_word(dev)
+
+    def forward(self, field, u, v, dt):
+        rc = _lib.lib().paradis_sl_advect_fwd(C.byref(self.g), _ptr(field), _ptr(u), _ptr(v), _ptr(self.out), self.B,
+                                              self.V, field.stride(0), u.stride(0), v.stride(0), dt, self.interp,
+                                              self.pole_fix, self.math, _ptr(self.ws_f), self.ws_f.numel(),
+                                              _ptr(self.status), _stream(field))
+        _lib.check(rc, "paradis_sl_advect_fwd")
+        return self.out
+
+    def backward(self, grad_out, field, u, v, dt, phases=3):
+        rc = _lib.lib().paradis_sl_advect_bwd(C.byref(self.g), _ptr(grad_out), _ptr(field), _ptr(u), _ptr(v),
+                                              _ptr(self.gfield), _ptr(self.gu), _ptr(self.gv), self.B, self.V,
+                                              grad_out.stride(0), field.stride(0), u.stride(0), v.stride(0), dt,
+                                              self.interp, self.pole_fix, self.math, phases, _ptr(self.ws_b),
+                                              self.ws_b.numel(), _ptr(self.status), _stream(field))
+        _lib.check(rc, "paradis_sl_advect_bwd")
+        return self.gfield, self.gu, self.gv
