@@ -115,7 +115,13 @@ int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* field, const
  * grad_field may be NULL (skips the adjoint gather); grad_u and grad_v may both be NULL.
  * `phases` selects the kernels to enqueue: PARADIS_BWD_ARRIVAL (grad_u, grad_v and the row
  * classes of every arrival point, kept in the workspace), PARADIS_BWD_GATHER (grad_field
- * from the classes left in the SAME workspace by an earlier ARRIVAL call), or both. */
+ * from the classes left in the SAME workspace by an earlier ARRIVAL call), or both.
+ *
+ * `cfl_cells` > 0 (with phases == PARADIS_BWD_ALL) enables the fused single-pass backward for
+ * the mid-latitudes: it is the caller's bound on the great-circle displacement |(u, v)| * dt in
+ * units of the latitude spacing (the semi-Lagrangian CFL number).  The bound is checked on the
+ * device for every arrival point; planes that exceed it are transparently recomputed by the
+ * general two-kernel path, so results never depend on it -- only speed does.  <= 0 disables it. */
 #define PARADIS_BWD_ARRIVAL 1
 #define PARADIS_BWD_GATHER 2
 #define PARADIS_BWD_ALL 3
@@ -124,7 +130,7 @@ int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* grad_out,
                           const float* field, const float* u, const float* v, float* grad_field,
                           float* grad_u, float* grad_v, int B, int V, int64_t gout_sB,
                           int64_t field_sB, int64_t u_sB, int64_t v_sB, float dt, int interp,
-                          int pole_fix, int math, int phases, void* workspace,
+                          int pole_fix, int math, int phases, float cfl_cells, void* workspace,
                           size_t workspace_bytes, int32_t* status, void* stream);
 
 /* ---- Host-buffer entry (end-to-end path) --------------------------------------------
@@ -137,8 +143,8 @@ int paradis_sl_advect_fwd_bwd_host(const paradis_sl_geom* geom, const float* h_f
                                    const float* h_u, const float* h_v, const float* h_grad_out,
                                    float* h_out, float* h_grad_field, float* h_grad_u,
                                    float* h_grad_v, int64_t planes, float dt, int interp,
-                                   int pole_fix, int math, int chunk_planes, void* d_scratch,
-                                   size_t scratch_bytes);
+                                   int pole_fix, int math, float cfl_cells, int chunk_planes,
+                                   void* d_scratch, size_t scratch_bytes);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ class NeuralSemiLagrangian(torch.nn.Module):
 
     def __init__(self, cfg, hidden_dim: int, mesh_size: tuple, num_vels: int, lat_grid: torch.Tensor,
                  lon_grid: torch.Tensor, interpolation: str = "bicubic", math: str = "fast",
-                 block_factory=None):
+                 block_factory=None, cfl_cells: float = 8.0):
         super().__init__()
         if interpolation not in ("bilinear", "bicubic"):
             raise ValueError(f"interpolation must be 'bilinear' or 'bicubic', got {interpolation!r}")
@@ -30,6 +30,7 @@ class NeuralSemiLagrangian(torch.nn.Module):
         self.mesh_size = mesh_size
         self.interpolation = interpolation
         self.math = math
+        self.cfl_cells = float(cfl_cells)  # backward performance hint, see ops.sl_advect
 
         block = block_factory or resolve_block_factory()
         adv_cfg = cfg.model.physblock.advection
@@ -87,5 +88,6 @@ class NeuralSemiLagrangian(torch.nn.Module):
     def forward(self, hidden_features: torch.Tensor, u: torch.Tensor, v: torch.Tensor, dt: float) -> torch.Tensor:
         """Compute advection using rotated coordinate system."""
         projected = self.down_projection(hidden_features)
-        advected = sl_advect(projected, u, v, self.geometry(), dt, self.interpolation, True, self.math)
+        advected = sl_advect(projected, u, v, self.geometry(), dt, self.interpolation, True, self.math,
+                             self.cfl_cells)
         return self.up_projection(advected)

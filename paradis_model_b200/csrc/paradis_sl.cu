@@ -18,6 +18,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
+#include <vector>
 
 #include "../../include/paradis_sl.h"
 #include "sl_device.cuh"
@@ -159,18 +161,21 @@ __device__ __forceinline__ void velocity_grads(const Params& P, const Traj& t, f
   gv = -P.dt * fmaf(kx, dlam_da, ky * ds_da);
 }
 
+#include "sl_sweep.cuh"
+
 template <bool EXACT, int INTERP, int VEC>
 __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
   const int c = blockIdx.y, b = blockIdx.z, pl = b * P.V + c;
+  if (P.plane_filter && !P.plane_filter[pl]) return;   // uniform per block
   const unsigned unit = blockIdx.x * blockDim.x + threadIdx.x;
   int reach = 0;
-  if (unit < (unsigned)(P.arrN * P.upr)) {
+  if (unit < (unsigned)(P.it_arrN * P.upr)) {
     const unsigned r = P.w4_mul ? fast_div(unit, P.w4_mul, P.w4_shift) : unit / (unsigned)P.upr;
     const int x = (unit - r * P.upr) * VEC;
-    const int y = P.arr0 + (int)r;  // global arrival row
-    const bool own = (y >= P.own0) && (y < P.own0 + P.ownN) && (P.gu != nullptr);
+    const int y = P.it_arr0 + (int)r;  // global arrival row
+    const bool own = (y >= P.it_own0) && (y < P.it_own0 + P.it_ownN) && (P.gu != nullptr);
     const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
-    const int aoff = (int)r * P.W + x;
+    const int aoff = (y - P.arr0) * P.W + x;
     const float* up = plane_ptr_bc(P.u, P.u_sB, b, c, P.arrN, P.W) + aoff;
     const float* vp = plane_ptr_bc(P.v, P.v_sB, b, c, P.arrN, P.W) + aoff;
     float uu[VEC], vv[VEC], ll[VEC], gg[VEC], ou[VEC], ov[VEC];
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
       }
     }
     if (P.cls) {
-      signed char* cp8 = P.cls + ((long long)pl * P.arrN + r) * P.W + x;
+      signed char* cp8 = P.cls + ((long long)pl * P.arrN + (y - P.arr0)) * P.W + x;
       if (VEC == 4) *reinterpret_cast<char4*>(cp8) = make_char4(cc[0], cc[1], cc[2], cc[3]);
       else {
 #pragma unroll
@@ -253,13 +258,18 @@ __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
 }
 
 __global__ void plane_reach_kernel(const unsigned char* __restrict__ blkmax, int nblk, int planes,
-                                   int* __restrict__ plane_reach) {
+                                   int* __restrict__ plane_reach, const unsigned char* __restrict__ filter,
+                                   unsigned char* __restrict__ flag, int limit) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= planes) return;
+  if (filter && !filter[warp]) return;
   int m = 0;
   for (int i = lane; i < nblk; i += 32) m = max(m, (int)blkmax[(long long)warp * nblk + i]);
   m = __reduce_max_sync(0xffffffffu, m);
-  if (lane == 0) plane_reach[warp] = m;
+  if (lane == 0) {
+    plane_reach[warp] = m;
+    if (flag && m > limit) flag[warp] = 1;   // contract of the fused sweep violated by this plane
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -356,9 +366,10 @@ __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const 
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pl = blockIdx.y;
-  const int lr = blockIdx.x * kGatherWarps + warp;  // local output row
-  if (lr >= P.ownN) return;
-  const int r = P.own0 + lr;                         // global output row
+  if (P.plane_filter && !P.plane_filter[pl]) return;
+  const int lr = blockIdx.x * kGatherWarps + warp;  // row within the iteration window
+  if (lr >= P.it_ownN) return;
+  const int r = P.it_own0 + lr;                      // global output row
   float* acc = smem + (size_t)warp * (P.W + kQueue);
   unsigned* queue = reinterpret_cast<unsigned*>(acc + P.W);
   for (int x = lane; x < P.W; x += 32) acc[x] = 0.0f;
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const 
     else { const int i = 2 * (P.H - 1) - r; if (i < P.H || i >= P.H + P.p) continue; Rd = i + P.p; shift = P.halfW; }
     // arrival rows y with floor(iy) + OMIN <= Rd <= floor(iy) + OMIN + NT - 1, floor(iy) = y + p + class
     int ylo = Rd - P.p - (OMIN + NT - 1) - reach, yhi = Rd - P.p - OMIN + reach;
-    ylo = max(ylo, P.arr0); yhi = min(yhi, P.arr0 + P.arrN - 1);
+    ylo = max(ylo, P.it_arr0); yhi = min(yhi, P.it_arr0 + P.it_arrN - 1);
     int qn = 0;
     for (int y = ylo; y <= yhi; ++y) {
       const signed char* crow = cls + (long long)(y - P.arr0) * P.W;
@@ -422,7 +433,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const 
     if (qn) gather_chunk<EXACT, INTERP>(P, pl, Rd, shift, acc, queue, qn, lane);
   }
   // adjoint of the first enforce_pole_continuity (advection.py:129): pole rows get their mean
-  float* orow = P.gfield + ((long long)pl * P.ownN + lr) * P.W;
+  float* orow = P.gfield + ((long long)pl * P.ownN + (r - P.own0)) * P.W;
   if (P.pole_fix && (r == 0 || r == P.H - 1)) {
     const float m = warp_row_sum(acc, P.W, lane) / (float)P.W;
     for (int x = lane; x < P.W; x += 32) orow[x] = m;
@@ -500,6 +511,7 @@ static int fill_params(Params& P, const paradis_sl_geom* g, int B, int V, float 
   P.H = g->H; P.W = g->W; P.p = p; P.Hp = g->H + 2 * p; P.Wp = g->W + 2 * p; P.halfW = g->W / 2;
   P.own0 = g->own_row0; P.ownN = g->own_rows; P.arr0 = g->arr_row0; P.arrN = g->arr_rows;
   P.fld0 = g->fld_row0; P.fldN = g->fld_rows;
+  P.it_own0 = P.own0; P.it_ownN = P.ownN; P.it_arr0 = P.arr0; P.it_arrN = P.arrN;
   P.sin_lat = g->sin_lat; P.cos_lat = g->cos_lat; P.lon = g->lon;
   P.min_lat = g->min_lat; P.d_lat = g->d_lat; P.min_lon = g->min_lon; P.d_lon = g->d_lon;
   P.dt = dt;
@@ -577,8 +589,9 @@ extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* f
   return check_launch("paradis_sl_advect_fwd");
 }
 
-// workspace layout (backward): fmean | gmean | plane_reach | blkmax | cls
-struct BwdWs { size_t fmean, gmean, reach, blkmax, cls, total; int nblk; };
+// workspace layout (backward): fmean | gmean | plane_reach[3] | plane_flag | blkmax[3] | cls
+// (three reach / blkmax sets: the two polar caps run concurrently with the sweep, then the fallback)
+struct BwdWs { size_t fmean, gmean, reach, reach_stride, flag, blkmax, blkmax_stride, cls, total; int nblk; };
 static BwdWs bwd_layout(int B, int V, int arr_rows, int W) {
   BwdWs w;
   const size_t planes = (size_t)B * V;
@@ -587,8 +600,11 @@ static BwdWs bwd_layout(int B, int V, int arr_rows, int W) {
   size_t off = 0;
   w.fmean = off; off += align_up(planes * 2 * sizeof(float), 256);
   w.gmean = off; off += align_up(planes * 2 * sizeof(float), 256);
-  w.reach = off; off += align_up(planes * sizeof(int), 256);
-  w.blkmax = off; off += align_up(planes * (size_t)w.nblk, 256);
+  w.reach_stride = align_up(planes * sizeof(int), 256);
+  w.reach = off; off += 3 * w.reach_stride;
+  w.flag = off; off += align_up(planes, 256);
+  w.blkmax_stride = align_up(planes * (size_t)w.nblk, 256);
+  w.blkmax = off; off += 3 * w.blkmax_stride;
   w.cls = off; off += align_up(planes * (size_t)arr_rows * W, 256);
   w.total = off;
   return w;
@@ -598,19 +614,21 @@ extern "C" size_t paradis_sl_advect_bwd_workspace(int B, int V, int arr_rows, in
   return bwd_layout(B, V, arr_rows, W).total;
 }
 
+// General (two-kernel) backward over the iteration windows set in P.
 template <bool EXACT, int INTERP>
-static int launch_bwd(Params& P, int vec, cudaStream_t st, bool want_field, int phases) {
+static int launch_general(Params P, int vec, cudaStream_t st, bool want_field, int phases, int max_nblk) {
   const int planes = P.B * P.V;
-  set_units(P, vec, P.arrN);
-  const unsigned units = (unsigned)P.arrN * P.upr;
+  set_units(P, vec, P.it_arrN);
+  const unsigned units = (unsigned)P.it_arrN * P.upr;
   dim3 grid((units + 255) / 256, P.V, P.B);
-  if ((int)grid.x > P.nblk) return fail(PARADIS_ERR_WORKSPACE, "internal: blkmax layout");
+  if ((int)grid.x > max_nblk) return fail(PARADIS_ERR_WORKSPACE, "internal: blkmax layout");
   P.nblk = grid.x;
   if (phases & PARADIS_BWD_ARRIVAL) {
     if (vec == 4) sl_bwd_arrival_kernel<EXACT, INTERP, 4><<<grid, 256, 0, st>>>(P);
     else sl_bwd_arrival_kernel<EXACT, INTERP, 1><<<grid, 256, 0, st>>>(P);
     if (want_field)
-      plane_reach_kernel<<<(planes * 32 + 255) / 256, 256, 0, st>>>(P.blkmax, P.nblk, planes, P.plane_reach);
+      plane_reach_kernel<<<(planes * 32 + 255) / 256, 256, 0, st>>>(P.blkmax, P.nblk, planes, P.plane_reach,
+                                                                   P.plane_filter, P.plane_flag, P.reach_limit);
   }
   if (!want_field || !(phases & PARADIS_BWD_GATHER)) return PARADIS_OK;
   const size_t smem = (size_t)kGatherWarps * (P.W + kQueue) * sizeof(float);
@@ -618,16 +636,188 @@ static int launch_bwd(Params& P, int vec, cudaStream_t st, bool want_field, int 
   auto kern = sl_bwd_gather_kernel<EXACT, INTERP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(PARADIS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  dim3 ggrid((P.ownN + kGatherWarps - 1) / kGatherWarps, planes);
+  dim3 ggrid((P.it_ownN + kGatherWarps - 1) / kGatherWarps, planes);
   kern<<<ggrid, kGatherWarps * 32, smem, st>>>(P);
   return PARADIS_OK;
+}
+
+// ---- plan of the fused sweep -------------------------------------------------------------------
+// cfl_cells bounds the great-circle displacement |(u, v)| * dt in units of the latitude spacing.
+// From it: the row reach rr, and per arrival row the longitudinal reach in cells (it grows as
+// 1 / cos(lat), see halo_cells()).  Destination rows all of whose arrival rows have a reach of at
+// most kSweepMaxHalo are swept; they are cut into bands of equal cost, enough of them to fill the
+// GPU about once.
+constexpr int kSweepMaxHalo = 32;
+constexpr int kSweepStrip = 128;
+
+template <int INTERP>
+static bool plan_sweep(const Params& P, float cfl_cells, int planes, int capacity_warps, SweepPlan& S, int& lo,
+                       int& hi) {
+  constexpr int NT = Stencil<INTERP>::NT;
+  const int H = P.H, W = P.W, wc = kSweepStrip;
+  if (!(cfl_cells > 0.0f) || H < 8) return false;
+  const double dphi = (double)P.d_lat / (H - 1), dlam = (double)P.d_lon / (W - 1);
+  const double delta = (double)cfl_cells * dphi;
+  const int rr = (int)ceil((double)cfl_cells);
+  if (rr > 40 || delta > 0.7) return false;
+  const int yh = rr + NT;                      // arrival rows either side that can reach a destination row
+  S.reach.sin_delta = (float)sin(delta); S.reach.cos_delta = (float)cos(delta);
+  S.reach.inv_dlam = (float)(1.0 / dlam); S.reach.extra = NT + 2;
+  S.reach.max_halo = kSweepMaxHalo;
+  while (wc + 2 * (S.reach.max_halo + 16) > W && S.reach.max_halo > 16) S.reach.max_halo -= 16;
+  if (wc + 2 * (S.reach.max_halo + 16) > W) return false;
+  std::vector<int> need(H);
+  for (int y = 0; y < H; ++y) {
+    const double lat = (double)P.min_lat + y * dphi;
+    need[y] = halo_cells(S.reach, (float)sin(lat), (float)cos(lat));
+  }
+  // a destination row is sweepable if every arrival row that can reach it fits the halo limit with a
+  // margin of one 16-column step (the device re-evaluates halo_cells from its own fp32 tables)
+  std::vector<char> okrow(H, 0);
+  for (int i = yh + 1; i < H - yh - 1; ++i) {
+    int n = 0;
+    for (int y = i - yh; y <= i + yh; ++y) n = n > need[y] ? n : need[y];
+    okrow[i] = n <= S.reach.max_halo;
+  }
+  const int own_lo = P.own0, own_hi = P.own0 + P.ownN;
+  lo = hi = -1;
+  {
+    int best = 0, start = -1;
+    for (int i = own_lo; i <= own_hi; ++i) {
+      const bool ok = i < own_hi && okrow[i];
+      if (ok && start < 0) start = i;
+      if (!ok && start >= 0) {
+        if (i - start > best) { best = i - start; lo = start; hi = i; }
+        start = -1;
+      }
+    }
+    if (best < 4 * yh) return false;           // not worth a sweep
+  }
+  const int nstrips = (W + wc - 1) / wc;
+  const int ncore = wc / 32;
+  auto row_cost = [&](int y) { return (double)(ncore + (2 * (need[y] < 1024 ? need[y] : 1024) + 31) / 32); };
+  double total = 0.0;
+  for (int i = lo; i < hi; ++i) total += row_cost(i);
+  int nb = capacity_warps / (planes * nstrips);  // bands so that all tasks are resident at once
+  if (nb < 1) nb = 1;
+  while (nb > 1 && (hi - lo) / nb < 4 * yh) --nb;  // keep the row halo a minor cost
+  if (nb > kMaxBands) nb = kMaxBands;
+  S.nbands = nb;
+  {
+    int i = lo; double accum = 0.0;
+    for (int k = 0; k < nb; ++k) {
+      S.ra[k] = (short)i;
+      const double goal = total * (k + 1) / nb;
+      while (i < hi && (accum + row_cost(i) <= goal || i == S.ra[k])) { accum += row_cost(i); ++i; }
+      if (k == nb - 1) i = hi;
+      S.rb[k] = (short)i;
+    }
+  }
+  S.nstrips = nstrips; S.wc = wc; S.rr = rr; S.ring = 2 * rr + NT; S.pitch = wc + 2 * (NT - 1);
+  S.planes = planes;
+  return true;
+}
+
+// Side streams for the two polar caps (they run beside the sweep, which leaves issue slots idle).
+// Created once per host thread and device; fork/join with events, so the call stays asynchronous
+// and capturable.  This is the only resource the library keeps between calls.
+struct SideStreams { bool ok = false; cudaStream_t s[2]; cudaEvent_t fork, join[2]; };
+static SideStreams* side_streams() {
+  static thread_local SideStreams ctx[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStreams& c = ctx[dev];
+  if (!c.ok) {
+    bool good = true;
+    for (int i = 0; i < 2; ++i) {
+      good = good && cudaStreamCreateWithFlags(&c.s[i], cudaStreamNonBlocking) == cudaSuccess;
+      good = good && cudaEventCreateWithFlags(&c.join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    good = good && cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess;
+    if (!good) { cudaGetLastError(); return nullptr; }
+    c.ok = true;
+  }
+  return &c;
+}
+
+static int device_capacity(const void* kern, int threads, size_t smem, int& nsm) {
+  int dev = 0, blocks = 0;
+  nsm = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, threads, smem) != cudaSuccess) return 0;
+  return blocks;
+}
+
+template <bool EXACT, int INTERP>
+static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_cells, const BwdWs& L, char* ws) {
+  const bool want_field = P.gfield != nullptr;
+  const int planes = P.B * P.V;
+  P.plane_filter = nullptr; P.plane_flag = nullptr; P.reach_limit = 1 << 20;
+  if (!want_field || phases != PARADIS_BWD_ALL || !(cfl_cells > 0.0f))
+    return launch_general<EXACT, INTERP>(P, vec, st, want_field, phases, L.nblk);
+
+  // ---- fused sweep over the mid-latitudes
+  constexpr int NT = Stencil<INTERP>::NT;
+  SweepPlan S;
+  memset(&S, 0, sizeof(S));
+  auto kern = sl_bwd_sweep_kernel<EXACT, INTERP>;
+  const int rr = (int)ceil((double)cfl_cells);
+  const int pitch = kSweepStrip + 2 * (NT - 1), cells = (2 * rr + NT) * pitch;
+  const size_t smem = (size_t)kSweepWarps * (cells + (kTagRows * pitch + 3) / 4) * sizeof(float);
+  int lo = -1, hi = -1, nsm = 148;
+  bool ok = smem <= 200 * 1024;
+  if (ok) ok = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+  int blocks_per_sm = ok ? device_capacity((const void*)kern, kSweepWarps * 32, smem, nsm) : 0;
+  ok = ok && blocks_per_sm > 0 && plan_sweep<INTERP>(P, cfl_cells, planes, blocks_per_sm * nsm * kSweepWarps, S, lo, hi);
+  if (!ok) {
+    cudaGetLastError();
+    return launch_general<EXACT, INTERP>(P, vec, st, want_field, phases, L.nblk);
+  }
+  unsigned char* flag = (unsigned char*)(ws + L.flag);
+  cudaMemsetAsync(flag, 0, planes, st);
+  S.plane_flag = flag; S.out0 = P.own0; S.outN = P.ownN;
+
+  // ---- the caps (rows the sweep does not own): general path on row sub-windows, on side streams
+  SideStreams* side = side_streams();
+  if (side) cudaEventRecord(side->fork, st);
+  const int yh = rr + NT + 1;
+  const int own_hi = P.own0 + P.ownN, arr_hi = P.arr0 + P.arrN;
+  const int sub[2][2] = {{P.own0, lo}, {hi, own_hi}};
+  bool forked[2] = {false, false};
+  for (int k = 0; k < 2; ++k) {
+    if (sub[k][1] <= sub[k][0]) continue;
+    Params Q = P;
+    Q.it_own0 = sub[k][0]; Q.it_ownN = sub[k][1] - sub[k][0];
+    int a0 = sub[k][0] - yh, a1 = sub[k][1] + yh;
+    if (a0 < P.arr0) a0 = P.arr0;
+    if (a1 > arr_hi) a1 = arr_hi;
+    Q.it_arr0 = a0; Q.it_arrN = a1 - a0;
+    Q.plane_flag = flag; Q.reach_limit = rr;       // a cap row reaching further than the contract: redo the plane
+    Q.plane_reach = (int*)(ws + L.reach + (k + 1) * L.reach_stride);
+    Q.blkmax = (unsigned char*)(ws + L.blkmax + (k + 1) * L.blkmax_stride);
+    cudaStream_t cs = st;
+    if (side) { cs = side->s[k]; cudaStreamWaitEvent(cs, side->fork, 0); forked[k] = true; }
+    if (int rc = launch_general<EXACT, INTERP>(Q, vec, cs, true, PARADIS_BWD_ALL, L.nblk)) return rc;
+    if (side) cudaEventRecord(side->join[k], cs);
+  }
+  const unsigned nblocks = (unsigned)((S.nbands * planes * S.nstrips + kSweepWarps - 1) / kSweepWarps);
+  kern<<<nblocks, kSweepWarps * 32, smem, st>>>(P, S);
+  for (int k = 0; k < 2; ++k)
+    if (forked[k]) cudaStreamWaitEvent(st, side->join[k], 0);
+  // ---- planes that broke the contract are recomputed entirely by the general path
+  Params Q = P;
+  Q.plane_filter = flag;
+  Q.gu = nullptr; Q.gv = nullptr;                   // grad_u / grad_v are already complete
+  return launch_general<EXACT, INTERP>(Q, vec, st, true, PARADIS_BWD_ALL, L.nblk);
 }
 
 extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* grad_out, const float* field,
                                      const float* u, const float* v, float* grad_field, float* grad_u,
                                      float* grad_v, int B, int V, int64_t gout_sB, int64_t field_sB, int64_t u_sB,
                                      int64_t v_sB, float dt, int interp, int pole_fix, int math, int phases,
-                                     void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
+                                     float cfl_cells, void* workspace, size_t workspace_bytes, int32_t* status,
+                                     void* stream) {
   Params P;
   if (int rc = fill_params(P, geom, B, V, dt, interp, pole_fix)) return rc;
   if (!grad_out || !field || !u || !v) return fail(PARADIS_ERR_NULL_POINTER, "NULL tensor pointer");
@@ -661,9 +851,8 @@ extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* g
   const int vec = vec_ok ? 4 : 1;
   const bool exact = math == PARADIS_MATH_EXACT;
   int rc;
-  const bool wf = grad_field != nullptr;
-  if (interp == 1) rc = exact ? launch_bwd<true, 1>(P, vec, st, wf, phases) : launch_bwd<false, 1>(P, vec, st, wf, phases);
-  else             rc = exact ? launch_bwd<true, 2>(P, vec, st, wf, phases) : launch_bwd<false, 2>(P, vec, st, wf, phases);
+  if (interp == 1) rc = exact ? launch_bwd<true, 1>(P, vec, st, phases, cfl_cells, L, ws) : launch_bwd<false, 1>(P, vec, st, phases, cfl_cells, L, ws);
+  else             rc = exact ? launch_bwd<true, 2>(P, vec, st, phases, cfl_cells, L, ws) : launch_bwd<false, 2>(P, vec, st, phases, cfl_cells, L, ws);
   if (rc) return rc;
   return check_launch("paradis_sl_advect_bwd");
 }
@@ -723,7 +912,8 @@ extern "C" size_t paradis_sl_host_scratch_bytes(int H, int W, int chunk_planes) 
 extern "C" int paradis_sl_advect_fwd_bwd_host(const paradis_sl_geom* geom, const float* h_field, const float* h_u,
                                               const float* h_v, const float* h_grad_out, float* h_out,
                                               float* h_grad_field, float* h_grad_u, float* h_grad_v, int64_t planes,
-                                              float dt, int interp, int pole_fix, int math, int chunk_planes,
+                                              float dt, int interp, int pole_fix, int math, float cfl_cells,
+                                              int chunk_planes,
                                               void* d_scratch, size_t scratch_bytes) {
   if (!geom) return fail(PARADIS_ERR_NULL_POINTER, "geom is NULL");
   if (!h_field || !h_u || !h_v || !h_grad_out || !h_out || !h_grad_field || !h_grad_u || !h_grad_v)
@@ -761,7 +951,7 @@ extern "C" int paradis_sl_advect_fwd_bwd_host(const paradis_sl_geom* geom, const
     if (rc) break;
     cudaMemcpyAsync(h_out + off, dout, bytes, cudaMemcpyDeviceToHost, s);
     rc = paradis_sl_advect_bwd(geom, dg, df, du, dv, dgf, dgu, dgv, 1, c, sB, sB, sB, sB, dt, interp, pole_fix, math,
-                               PARADIS_BWD_ALL, base + L.wsb, paradis_sl_advect_bwd_workspace(1, c, H, W), nullptr, s);
+                               PARADIS_BWD_ALL, cfl_cells, base + L.wsb, paradis_sl_advect_bwd_workspace(1, c, H, W), nullptr, s);
     if (rc) break;
     cudaMemcpyAsync(h_grad_field + off, dgf, bytes, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(h_grad_u + off, dgu, bytes, cudaMemcpyDeviceToHost, s);

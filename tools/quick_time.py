@@ -23,11 +23,14 @@ for name, H, W, B, V, poles in cases:
     pts = B * V * H * W
     for interp in ("bilinear", "bicubic"):
         for math in ("fast", "exact"):
-            R = RawAdvection(geo, B, V, interp, True, math)
+            R = RawAdvection(geo, B, V, interp, True, math, 0.0)
             tf = timeit(lambda: R.forward(f, u, v, S.DT_DEFAULT))
             ta = timeit(lambda: R.backward(g, f, u, v, S.DT_DEFAULT, 1))
             tg = timeit(lambda: R.backward(g, f, u, v, S.DT_DEFAULT, 2))
-            tot = tf + ta + tg
+            R2 = RawAdvection(geo, B, V, interp, True, math, 6.0)
+            ts = timeit(lambda: R2.backward(g, f, u, v, S.DT_DEFAULT, 3))
+            tot = tf + ts
             print(f"{name} {interp:8s} {math:5s}: fwd {tf:.3f} ms ({16*pts/tf/1e6:.0f} GB/s) arrival {ta:.3f} ms "
-                  f"gather {tg:.3f} ms total {tot:.3f} ms -> {pts/tot/1e6:.1f} Gpt/s, {44*pts/tot/1e6:.0f} GB/s", flush=True)
+                  f"gather {tg:.3f} ms | fused bwd {ts:.3f} ms ({28*pts/ts/1e6:.0f} GB/s) total {tot:.3f} ms -> "
+                  f"{pts/tot/1e6:.1f} Gpt/s, {44*pts/tot/1e6:.0f} GB/s", flush=True)
     P.check_status()
