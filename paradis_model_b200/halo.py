@@ -1,0 +1,214 @@
+"""Latitude-band decomposition of one 0.25-degree field across GPUs.
+
+Rank k of G owns a contiguous band of full longitude circles.  Because every band holds whole
+circles, the longitude wrap and the 180-degree pole shift of the GeoCyclic map stay local; the pole
+reflection rows and the pole-mean rows belong to the first / last band.  The only exchange is with
+the two latitude neighbours:
+
+  forward : `halo` rows of `field` either side (departure stencils reach at most cfl + stencil rows)
+  backward: `halo` rows of (grad_out, u, v) either side, so that every band computes its own
+            grad_field rows with the deterministic inverse-stencil gather -- one exchange, no
+            reverse add, bit-identical to the single-GPU result for the general path.
+
+The exchange is point-to-point (`torch.distributed.batch_isend_irecv`: NCCL send/recv over NVLink on
+GPUs, gloo in the CPU tests).  There is no collective on the data path.  The reference has no
+spatial decomposition at all (its only parallelism is DDP, train.py:49); this module is new.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+STENCIL_ROWS = {"bilinear": 2, "bicubic": 4}
+
+
+@dataclass
+class BandPlan:
+    H: int
+    W: int
+    rank: int
+    world: int
+    row0: int          # first owned row (global)
+    rows: int          # owned rows
+    halo: int          # rows exchanged with each neighbour
+    lo: int            # rows received from the southern neighbour (0 for the first band)
+    hi: int            # rows received from the northern neighbour (0 for the last band)
+
+    @property
+    def ext_row0(self) -> int:
+        return self.row0 - self.lo
+
+    @property
+    def ext_rows(self) -> int:
+        return self.lo + self.rows + self.hi
+
+    def windows(self) -> Tuple[Tuple[int, int], Tuple[int, int]]:
+        """(own, ext) as (row0, rows) pairs for SLGeometry.band()."""
+        return (self.row0, self.rows), (self.ext_row0, self.ext_rows)
+
+
+def band_rows(H: int, world: int) -> List[Tuple[int, int]]:
+    """Split H rows into `world` contiguous bands of (almost) equal height."""
+    base, rem = divmod(H, world)
+    out, r = [], 0
+    for k in range(world):
+        n = base + (1 if k < rem else 0)
+        out.append((r, n))
+        r += n
+    return out
+
+
+def halo_rows(cfl_cells: float, interpolation: str) -> int:
+    """Rows a departure stencil can reach beyond its arrival row: ceil(cfl) for the trajectory plus
+    the stencil extent (and one row of slack for the floor)."""
+    return int(math.ceil(cfl_cells)) + STENCIL_ROWS[interpolation] + 1
+
+
+def make_plan(H: int, W: int, rank: int, world: int, cfl_cells: float, interpolation: str = "bilinear") -> BandPlan:
+    bands = band_rows(H, world)
+    row0, rows = bands[rank]
+    halo = halo_rows(cfl_cells, interpolation)
+    if world > 1 and min(n for _, n in bands) < halo:
+        raise ValueError(f"bands of {min(n for _, n in bands)} rows are thinner than the halo ({halo} rows): "
+                         "use fewer ranks or a smaller cfl_cells")
+    lo = halo if rank > 0 else 0
+    hi = halo if rank < world - 1 else 0
+    return BandPlan(H, W, rank, world, row0, rows, halo, lo, hi)
+
+
+def exchange_rows(x: torch.Tensor, plan: BandPlan, group=None) -> torch.Tensor:
+    """x: [B, C, rows, W] owned rows -> [B, C, lo + rows + hi, W] with the neighbours' boundary rows.
+
+    One send and one receive per neighbour, batched (NCCL groups them into one launch)."""
+    if plan.world == 1:
+        return x
+    B, C, n, W = x.shape
+    assert n == plan.rows and W == plan.W
+    ext = x.new_empty((B, C, plan.ext_rows, W))
+    ext[:, :, plan.lo:plan.lo + n] = x
+    ops, keep = [], []
+    h = plan.halo
+    if plan.rank > 0:                                   # southern neighbour
+        send = x[:, :, :h].contiguous()
+        recv = x.new_empty((B, C, h, W))
+        ops += [dist.P2POp(dist.isend, send, plan.rank - 1, group), dist.P2POp(dist.irecv, recv, plan.rank - 1, group)]
+        keep.append(("lo", recv))
+    if plan.rank < plan.world - 1:                      # northern neighbour
+        send = x[:, :, n - h:].contiguous()
+        recv = x.new_empty((B, C, h, W))
+        ops += [dist.P2POp(dist.isend, send, plan.rank + 1, group), dist.P2POp(dist.irecv, recv, plan.rank + 1, group)]
+        keep.append(("hi", recv))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for side, recv in keep:
+        if side == "lo":
+            ext[:, :, :plan.lo] = recv
+        else:
+            ext[:, :, plan.lo + n:] = recv
+    return ext
+
+
+class _LatBandFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, field, u, v, geometry, plan, dt, interp, pole_fix, math, cfl, group):
+        from . import _lib
+        own, ext = plan.windows()
+        f_ext = exchange_rows(field, plan, group)
+        g = geometry.band(own, own, ext)
+        out = torch.ops.paradis.sl_advect(f_ext, u, v, g.tables, g.scalars, dt, _lib.INTERP[interp], pole_fix,
+                                          _lib.MATH[math], g.windows, cfl)
+        ctx.save_for_backward(f_ext, u, v)
+        ctx.meta = (geometry, plan, dt, interp, pole_fix, math, cfl, group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import _lib
+        f_ext, u, v = ctx.saved_tensors
+        geometry, plan, dt, interp, pole_fix, math, cfl, group = ctx.meta
+        own, ext = plan.windows()
+        V = u.shape[1]
+        packed = exchange_rows(torch.cat([grad_out.contiguous(), u, v], dim=1), plan, group)   # one message per side
+        g_ext, u_ext, v_ext = packed[:, :V], packed[:, V:2 * V], packed[:, 2 * V:]
+        g = geometry.band(own, ext, ext)
+        gf, gu, gv = torch.ops.paradis.sl_advect_backward(g_ext, f_ext, u_ext, v_ext, g.tables, g.scalars, dt,
+                                                          _lib.INTERP[interp], pole_fix, _lib.MATH[math], g.windows,
+                                                          cfl, True, True)
+        return gf, gu, gv, None, None, None, None, None, None, None, None
+
+
+def lat_band_advect(field, u, v, geometry, plan: BandPlan, dt: float, interpolation="bilinear", pole_fix=True,
+                    math="fast", cfl_cells: float = 8.0, group=None):
+    """sl_advect on this rank's latitude band: field, u, v, result are [B, V, plan.rows, W].
+
+    `cfl_cells` sizes the halo (plan.halo must have been built with the same value): unlike the
+    single-GPU call it is a CONTRACT here -- a departure stencil that leaves the halo sets the
+    device status word (paradis_model_b200.check_status raises DISPLACEMENT)."""
+    return _LatBandFn.apply(field, u, v, geometry, plan, float(dt), interpolation, bool(pole_fix), math,
+                            float(cfl_cells), group)
+
+
+# ------------------------------------------------------------------------------------------
+# strong-scaling benchmark leg (bench.py --decomp latband)
+# ------------------------------------------------------------------------------------------
+def bench_latband(args, workload, rank, world, dev):
+    import json
+    import time
+    import paradis_model_b200 as P
+    from . import synthetic as S
+    from bench import BYTES_STEP, CFL_CELLS, measured_peak
+
+    H, W, V, Bg, poles = workload
+    dt = S.DT_DEFAULT
+    lat, lon = S.make_grids(H, W, poles)
+    geo = P.SLGeometry.from_grids(lat.to(dev), lon.to(dev))
+    plan = make_plan(H, W, rank, world, CFL_CELLS, args.interp)
+    # every rank draws the same global tensors (same seed) and keeps its band: the global problem is
+    # identical for every N (strong scaling)
+    full = S.white_noise_inputs(H, W, Bg, V, dt, seed=0)
+    sl = slice(plan.row0, plan.row0 + plan.rows)
+    field, u, v, go = [t[:, :, sl].contiguous().to(dev) for t in full]
+    del full
+
+    def step():
+        f = field.requires_grad_(True)
+        uu, vv = u.requires_grad_(True), v.requires_grad_(True)
+        out = lat_band_advect(f, uu, vv, geo, plan, dt, args.interp, True, args.math, CFL_CELLS)
+        out.backward(go)
+        f.grad = uu.grad = vv.grad = None
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    P.check_status(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    if rank == 0:
+        pts = Bg * V * H * W
+        peak, src = measured_peak()
+        gbs = BYTES_STEP * pts / (ms_step * 1e-3) / 1e9
+        halo_bytes = 2 * plan.halo * W * V * Bg * 4
+        print(json.dumps({
+            "metric": "SL advection fwd+bwd grid-pts*ch/s", "value": pts / (ms_step * 1e-3), "unit": "grid-pt*ch/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {H}x{W} mesh, V={V}, batch {Bg} GLOBAL, {args.interp}, "
+                                   f"latitude bands x{world}, halo {plan.halo} rows",
+                       "parallelism": f"latband{world}: NCCL send/recv halo exchange, {halo_bytes} B per rank per "
+                                      f"forward (x3 in backward)"},
+            "roofline_step": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
+                              "frac": gbs / (peak * world), "peak_source": src}}), flush=True)
+    dist.destroy_process_group()
