@@ -147,7 +147,9 @@ __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
 __device__ __forceinline__ void velocity_grads(const Params& P, const Traj& t, float sp, float cp, float gix,
                                                float giy, float& gu, float& gv) {
   const float r2 = fmaf(t.num, t.num, t.den * t.den);
-  const float inv_r2 = r2 > 0.0f ? 1.0f / r2 : 0.0f;
+  float inv_r2;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_r2) : "f"(r2));
+  inv_r2 = r2 > 0.0f ? inv_r2 : 0.0f;
   const float cacb = t.ca * t.cb, casb = t.ca * t.sb, sasb = t.sa * t.sb, sacb = t.sa * t.cb;
   const float dlam_db = (t.den * cacb + t.num * casb * cp) * inv_r2;
   const float dlam_da = (-t.den * sasb + t.num * fmaf(sacb, cp, t.ca * sp)) * inv_r2;
@@ -754,7 +756,7 @@ static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_
   const bool want_field = P.gfield != nullptr;
   const int planes = P.B * P.V;
   P.plane_filter = nullptr; P.plane_flag = nullptr; P.reach_limit = 1 << 20;
-  if (!want_field || phases != PARADIS_BWD_ALL || !(cfl_cells > 0.0f))
+  if (!want_field || phases != PARADIS_BWD_ALL || !(cfl_cells > 0.0f) || vec != 4)   // the sweep needs float4 rows
     return launch_general<EXACT, INTERP>(P, vec, st, want_field, phases, L.nblk);
 
   // ---- fused sweep over the mid-latitudes

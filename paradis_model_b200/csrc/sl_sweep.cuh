@@ -77,6 +77,99 @@ __device__ __forceinline__ void resolve_clashes(int key, int tkey, unsigned char
   }
 }
 
+// Warp-uniform state of the row being swept.
+struct SweepRow {
+  const float* __restrict__ urow;
+  const float* __restrict__ vrow;
+  const float* __restrict__ grow;
+  float* __restrict__ gu_row;      // nullptr when this row's grad_u / grad_v are not produced here
+  float* __restrict__ gv_row;
+  float sp, cp;
+  int y, head, hx;
+};
+
+// What one lane contributes to the ring in one 32-lane step.
+template <int NT> struct StepOut {
+  int key;                         // ring cell of tap (0, 0), < 0: nothing to add
+  int slot0, cidx;
+  float cc[NT * NT];
+};
+
+// Trajectory, contract check, (for own points) grad_u / grad_v, and the stencil weights of one
+// arrival point.  x: column (unwrapped, for the ring index), xw: wrapped column.
+template <bool EXACT, int INTERP, bool CORE>
+__device__ __forceinline__ void sweep_compute(const Params& P, const SweepRow& R, const float* __restrict__ f,
+                                              float mean0, float mean1, int ja, int wc, int ring, int pitch, int rr,
+                                              int x, int xw, float uu, float vv, float g, float lonp, bool& violated,
+                                              StepOut<Stencil<INTERP>::NT>& o, float& ou, float& ov) {
+  constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
+  o.key = -1; o.slot0 = 0; o.cidx = 0;
+  Traj t;
+  trajectory<EXACT>(P, uu, vv, R.sp, R.cp, lonp, t);
+  const float fx = floorf(t.ix), fy = floorf(t.iy);
+  const float tx = __fsub_rn(t.ix, fx), ty = __fsub_rn(t.iy, fy);
+  const int x0 = (int)fx + OMIN;                 // padded column of tap 0
+  const int cls = (int)fy - (R.y + P.p);         // row class
+  int dx = x0 - P.p - xw;                        // longitudinal cell displacement of tap 0
+  if (dx < -P.halfW) dx += P.W; else if (dx >= P.halfW) dx -= P.W;
+  const bool in_ring = (unsigned)(cls + rr) <= (unsigned)(2 * rr);
+  if (CORE) {
+    // every arrival point a task sees in its own columns is checked against the contract
+    if (!in_ring || dx < -R.hx || dx > R.hx - NT + 1) violated = true;
+#ifndef PSL_DBG_NOGRADS
+    if (R.gu_row) {
+      float val, ddx, ddy;
+      stencil_eval<INTERP, true>(P, f, t, mean0, mean1, val, ddx, ddy);
+      velocity_grads(P, t, R.sp, R.cp, g * ddx, g * ddy, ou, ov);
+    }
+#endif
+  }
+  const int cidx = (x - ja) + dx + (NT - 1);     // ring column of tap 0
+  const bool hit = in_ring && (unsigned)cidx <= (unsigned)(wc + NT - 2);
+  float wx[NT], wy[NT], d0[NT], d1[NT];
+  axis_weights<INTERP, false>(tx, wx, d0);
+  axis_weights<INTERP, false>(ty, wy, d1);
+  int slot0 = R.head + cls + rr;
+  if (slot0 >= ring) slot0 -= ring;
+  o.slot0 = hit ? slot0 : 0; o.cidx = hit ? cidx : 0;
+  o.key = hit ? slot0 * pitch + cidx : -1;
+  const float gh = hit ? g : 0.0f;
+#pragma unroll
+  for (int a = 0; a < NT; ++a) {
+    const float gw = __fmul_rn(gh, wy[a]);
+#pragma unroll
+    for (int bb = 0; bb < NT; ++bb)   // padding_mode="zeros": only the last tap columns can leave the padded plane
+      o.cc[a * NT + bb] = (bb == 0 || x0 + bb < P.Wp) ? __fmul_rn(gw, wx[bb]) : 0.0f;
+  }
+}
+
+// Add one step's contributions to the ring: clash resolution, then NT*NT single-writer phases.
+template <int NT>
+__device__ __forceinline__ void sweep_scatter(StepOut<NT>& o, float* acc, unsigned char* tag, int ring, int pitch,
+                                              int lane) {
+  bool writer;
+#ifdef PSL_DBG_NOSCATTER
+  if (o.key != -12345) return;
+#endif
+#ifdef PSL_DBG_NOCLASH
+  writer = o.key >= 0;
+#else
+  resolve_clashes<NT>(o.key, (o.slot0 & (kTagRows - 1)) * pitch + o.cidx, tag, lane, o.cc, writer);
+#endif
+  float* base = acc + o.cidx;
+#pragma unroll
+  for (int a = 0; a < NT; ++a) {
+    int sl = o.slot0 + a;
+    if (sl >= ring) sl -= ring;
+    float* row = base + sl * pitch;
+#pragma unroll
+    for (int bb = 0; bb < NT; ++bb) {
+      if (writer) row[bb] += o.cc[a * NT + bb];
+      __syncwarp();
+    }
+  }
+}
+
 template <bool EXACT, int INTERP>
 __global__ void __launch_bounds__(kSweepWarps * 32) sl_bwd_sweep_kernel(const Params P, const SweepPlan S) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
@@ -102,116 +195,108 @@ __global__ void __launch_bounds__(kSweepWarps * 32) sl_bwd_sweep_kernel(const Pa
   const float* vp = plane_ptr_bc(P.v, P.v_sB, b, c, P.arrN, P.W);
   const float* gp = plane_ptr_bc(P.gout, P.gout_sB, b, c, P.arrN, P.W);
   const float* f = plane_ptr_bc(P.field, P.field_sB, b, c, P.fldN, P.W);
+  float* gu_pl = P.gu ? P.gu + (long long)pl * S.outN * P.W : nullptr;
+  float* gv_pl = P.gu ? P.gv + (long long)pl * S.outN * P.W : nullptr;
+  float* gf_pl = P.gfield + (long long)pl * S.outN * P.W + ja;
   float mean0 = 0.0f, mean1 = 0.0f;
   if (P.pole_fix) { mean0 = __ldg(P.fmean + 2 * pl); mean1 = __ldg(P.fmean + 2 * pl + 1); }
-  const bool want_uv = P.gu != nullptr;
-  const int ncore = (wc + 31) >> 5;
+  const int arr_lo = P.arr0, arr_hi = P.arr0 + P.arrN, W = P.W;
   bool violated = false;
 
   // destination row i_done(y) = y - rr + OMIN is complete after arrival row y; it sits in slot `head`
   const int y_first = ra - (ring - 1) + rr - OMIN, y_last = rb - 1 + rr - OMIN;
-  int head = 0;
+  SweepRow R;
+  R.head = 0;
   for (int y = y_first; y <= y_last; ++y) {
-    if (y >= P.arr0 && y < P.arr0 + P.arrN) {
-      const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
-      const int rowoff = (y - P.arr0) * P.W;
-      const bool core_row = (y >= ra) && (y < rb);
-      int hx = halo_cells(S.reach, sp, cp);           // <= max_halo for every row a band may visit
-      hx = min(hx, S.reach.max_halo + 16);            // (host/device rounding may differ by one step)
-      const int nhalo = (2 * hx + 31) >> 5;
-      for (int ch = 0; ch < ncore + nhalo; ++ch) {
-        // column of this lane: core chunks cover [ja, jb), halo chunks cover [ja-hx, ja) then [jb, jb+hx)
-        int x;
-        bool live, core = false, check = false;
-        if (ch < ncore) {
-          x = ja + (ch << 5) + lane;
-          live = x < jb;
-          core = live && core_row;
-          check = live;          // every arrival point this task sees in its own columns is checked
-        } else {
-          const int h = ((ch - ncore) << 5) + lane;
-          live = h < 2 * hx;
-          x = h < hx ? ja - hx + h : jb + (h - hx);
-        }
-        int xw = x;
-        if (xw < 0) xw += P.W; else if (xw >= P.W) xw -= P.W;
-        live = live && ((unsigned)xw < (unsigned)P.W);
-        float cc[NT * NT];
+    if (y >= arr_lo && y < arr_hi) {
+      R.y = y;
+      R.sp = __ldg(P.sin_lat + y); R.cp = __ldg(P.cos_lat + y);
+      const int rowoff = (y - arr_lo) * W;
+      R.urow = up + rowoff; R.vrow = vp + rowoff; R.grow = gp + rowoff;
+      const bool core_row = (y >= ra) && (y < rb) && gu_pl;
+      R.gu_row = core_row ? gu_pl + (y - S.out0) * W : nullptr;
+      R.gv_row = core_row ? gv_pl + (y - S.out0) * W : nullptr;
+      int hx = halo_cells(S.reach, R.sp, R.cp);       // <= max_halo for every row a band may visit
+      R.hx = min(hx, S.reach.max_halo + 16);          // (host/device rounding may differ by one step)
+      const int nhalo = (2 * R.hx + 31) >> 5;
+      if (NT == 2) {
+      // own columns: one step of 4 consecutive points per lane (float4 loads / stores, 4 independent
+        // trajectories in flight), scattered as 4 sub-steps of points 4 columns apart
+        {
+          const int x = ja + 4 * lane;
+          StepOut<NT> o[4];
 #pragma unroll
-        for (int t = 0; t < NT * NT; ++t) cc[t] = 0.0f;
-        int key = -1, slot0 = 0, cidx = 0;
-        if (live) {
-          const float uu = __ldg(up + rowoff + xw), vv = __ldg(vp + rowoff + xw);
-          const float g = __ldg(gp + rowoff + xw);
-          Traj t;
-          trajectory<EXACT>(P, uu, vv, sp, cp, __ldg(P.lon + xw), t);
-          const float fx = floorf(t.ix), fy = floorf(t.iy);
-          const float tx = __fsub_rn(t.ix, fx), ty = __fsub_rn(t.iy, fy);
-          const int x0 = (int)fx + OMIN;                 // padded column of tap 0
-          const int cls = (int)fy - (y + P.p);           // row class
-          int dx = x0 - P.p - xw;                        // longitudinal cell displacement of tap 0
-          if (dx < -P.halfW) dx += P.W; else if (dx >= P.halfW) dx -= P.W;
-          float wx[NT], wy[NT], dwx[NT], dwy[NT];
-          axis_weights<INTERP, true>(tx, wx, dwx);
-          axis_weights<INTERP, true>(ty, wy, dwy);
-          const bool in_ring = (unsigned)(cls + rr) <= (unsigned)(2 * rr);
-          if (check && (!in_ring || dx < -hx || dx > hx - NT + 1)) violated = true;
-          if (core) {
-            if (want_uv) {
-              float val, ddx, ddy;
-              stencil_eval<INTERP, true>(P, f, t, mean0, mean1, val, ddx, ddy);
-              float ou, ov;
-              velocity_grads(P, t, sp, cp, g * ddx, g * ddy, ou, ov);
-              const long long o = ((long long)pl * S.outN + (y - S.out0)) * P.W + xw;
-              __stcs(P.gu + o, ou);
-              __stcs(P.gv + o, ov);
+          for (int k = 0; k < 4; ++k) {
+            o[k].key = -1; o[k].slot0 = 0; o[k].cidx = 0;
+#pragma unroll
+            for (int t = 0; t < NT * NT; ++t) o[k].cc[t] = 0.0f;
+          }
+          if (x < jb) {
+            float uu[4], vv[4], gg[4], ll[4], ou[4], ov[4];
+            *reinterpret_cast<float4*>(uu) = __ldg(reinterpret_cast<const float4*>(R.urow + x));
+            *reinterpret_cast<float4*>(vv) = __ldg(reinterpret_cast<const float4*>(R.vrow + x));
+            *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(R.grow + x));
+            *reinterpret_cast<float4*>(ll) = __ldg(reinterpret_cast<const float4*>(P.lon + x));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              sweep_compute<EXACT, INTERP, true>(P, R, f, mean0, mean1, ja, wc, ring, pitch, rr, x + k, x + k, uu[k], vv[k],
+                                                 gg[k], ll[k], violated, o[k], ou[k], ov[k]);
+            if (R.gu_row) {
+              __stcs(reinterpret_cast<float4*>(R.gu_row + x), *reinterpret_cast<float4*>(ou));
+              __stcs(reinterpret_cast<float4*>(R.gv_row + x), *reinterpret_cast<float4*>(ov));
             }
           }
-          cidx = (x - ja) + dx + (NT - 1);               // ring column of tap 0
-          if (in_ring && (unsigned)cidx <= (unsigned)(wc + NT - 2)) {
-            slot0 = head + cls + rr;
-            if (slot0 >= ring) slot0 -= ring;
-            key = slot0 * pitch + cidx;
 #pragma unroll
-            for (int a = 0; a < NT; ++a)
-#pragma unroll
-              for (int bb = 0; bb < NT; ++bb)
-                cc[a * NT + bb] = g * __fmul_rn(wy[a], wx[bb]);
-            // padding_mode="zeros": only the last tap column can fall off the padded plane (x0 >= 0)
-            if (x0 + NT - 1 >= P.Wp) {
-#pragma unroll
-              for (int a = 0; a < NT; ++a)
-#pragma unroll
-                for (int bb = 0; bb < NT; ++bb)
-                  if (x0 + bb >= P.Wp) cc[a * NT + bb] = 0.0f;
-            }
-          }
+          for (int k = 0; k < 4; ++k) sweep_scatter<NT>(o[k], acc, tag, ring, pitch, lane);
         }
-        bool writer;
-        resolve_clashes<NT>(key, (slot0 & (kTagRows - 1)) * pitch + cidx, tag, lane, cc, writer);
+      } else {
+        // wide stencils: one point per lane and step (16 weights per point do not fit 4-fold in registers)
+        for (int ch = 0; ch < ((wc + 31) >> 5); ++ch) {
+          StepOut<NT> oa;
+          oa.key = -1; oa.slot0 = 0; oa.cidx = 0;
 #pragma unroll
-        for (int a = 0; a < NT; ++a) {
-          int sl = slot0 + a;
-          if (sl >= ring) sl -= ring;
-#pragma unroll
-          for (int bb = 0; bb < NT; ++bb) {
-            if (writer) acc[sl * pitch + cidx + bb] += cc[a * NT + bb];
-            __syncwarp();
+          for (int t = 0; t < NT * NT; ++t) oa.cc[t] = 0.0f;
+          const int xa = ja + (ch << 5) + lane;
+          if (xa < jb) {
+            float ou = 0.0f, ov = 0.0f;
+            sweep_compute<EXACT, INTERP, true>(P, R, f, mean0, mean1, ja, wc, ring, pitch, rr, xa, xa, __ldg(R.urow + xa),
+                                               __ldg(R.vrow + xa), __ldg(R.grow + xa), __ldg(P.lon + xa), violated, oa, ou,
+                                               ov);
+            if (R.gu_row) { __stcs(R.gu_row + xa, ou); __stcs(R.gv_row + xa, ov); }
           }
+          sweep_scatter<NT>(oa, acc, tag, ring, pitch, lane);
         }
+      }
+      // halo columns: [ja - hx, ja) then [jb, jb + hx), one point per lane
+      for (int ch = 0; ch < nhalo; ++ch) {
+        StepOut<NT> oa;
+        oa.key = -1; oa.slot0 = 0; oa.cidx = 0;
+#pragma unroll
+        for (int t = 0; t < NT * NT; ++t) oa.cc[t] = 0.0f;
+        const int h = (ch << 5) + lane;
+        const int xa = h < R.hx ? ja - R.hx + h : jb + (h - R.hx);
+        int xw = xa;
+        if (xw < 0) xw += W; else if (xw >= W) xw -= W;
+        if (h < 2 * R.hx) {
+          float ou, ov;
+          sweep_compute<EXACT, INTERP, false>(P, R, f, mean0, mean1, ja, wc, ring, pitch, rr, xa, xw, __ldg(R.urow + xw),
+                                              __ldg(R.vrow + xw), __ldg(R.grow + xw), __ldg(P.lon + xw), violated, oa, ou,
+                                              ov);
+        }
+        sweep_scatter<NT>(oa, acc, tag, ring, pitch, lane);
       }
     }
     // retire destination row i = y - rr + OMIN
     const int i = y - rr + OMIN;
-    float* row = acc + head * pitch;
+    float* row = acc + R.head * pitch;
     if (i >= ra && i < rb) {
-      float* orow = P.gfield + ((long long)pl * S.outN + (i - S.out0)) * P.W + ja;
+      float* orow = gf_pl + (i - S.out0) * W;
       for (int k = lane; k < wc; k += 32) orow[k] = row[k + NT - 1];
     }
     __syncwarp();
     for (int k = lane; k < pitch; k += 32) row[k] = 0.0f;
     __syncwarp();
-    head = head + 1 == ring ? 0 : head + 1;
+    R.head = R.head + 1 == ring ? 0 : R.head + 1;
   }
   if (__any_sync(0xffffffffu, violated) && lane == 0) S.plane_flag[pl] = 1;
 }

@@ -153,7 +153,8 @@ def test_zero_velocity_identity():
     out = P().sl_advect(f.cuda(), z.cuda(), z.cuda(), geo, DT, "bilinear").cpu()
     assert relmax(out, O.pole_mean(f)) < 1e-4      # white-noise field, coordinates good to ~1e-5 cells
     out = P().sl_advect(f.cuda(), z.cuda(), z.cuda(), geo, DT, "bilinear", True, "exact").cpu()
-    assert relmax(out, O.pole_mean(f)) < 2e-5
+    assert relmax(out, O.pole_mean(f)) < 5e-5      # the reference's own normalise/un-normalise round trip
+    assert relmax(out, O.sl_advect(f, z, z, lat, lon, DT, "bilinear")) < 1e-5
 
 
 def test_strided_velocity_views_and_no_pole_fix():
@@ -290,7 +291,9 @@ def test_module_drop_in_autograd_and_state_dict():
     proj = m.down_projection(hid.detach()).cpu()
     core = O.sl_advect(proj, velv[:, 0].detach().cpu(), velv[:, 1].detach().cpu(), lat, lon, DT, "bilinear")
     ref = m.up_projection(core.cuda())
-    assert bad_fraction(out.detach().cpu(), ref.detach().cpu(), 1e-4) < 1e-3
+    # white-noise field and velocities through a random 1x1 projection: fast-math coordinates differ from
+    # the CPU oracle by ~1e-5 cell, i.e. ~1e-4 of max|out| at the steepest points
+    assert bad_fraction(out.detach().cpu(), ref.detach().cpu(), 3e-4) < 1e-3
 
 
 # ------------------------------------------------------------------ fused backward sweep
