@@ -133,6 +133,15 @@ int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* grad_out,
                           int pole_fix, int math, int phases, float cfl_cells, void* workspace,
                           size_t workspace_bytes, int32_t* status, void* stream);
 
+/* Departure coordinates only (parity instrument): for every arrival point of the own window writes
+ * the 11 intermediates of model/advection.py:82-94,138-150 as planes
+ *   coords[B, V, 11, own_rows, W] = { ix, iy, sin(lat'), cos(lat'), sin(lon'), cos(lon'), sin_lat, num, den,
+ *                                    lat_dep, lon_dep }
+ * with ix, iy the sampler coordinates in the padded plane (what ATen floors, GridSampler.h:27-36). */
+int paradis_sl_departure_coords(const paradis_sl_geom* geom, const float* u, const float* v,
+                                float* coords, int B, int V, int64_t u_sB, int64_t v_sB, float dt,
+                                int interp, int math, void* stream);
+
 /* ---- Host-buffer entry (end-to-end path) --------------------------------------------
  * Same operator (single GPU, full mesh) with HOST pointers (pinned memory recommended):
  * the library stages `chunk_planes` (b, v) planes at a time through caller-provided

@@ -44,6 +44,8 @@ _PROTOS = {
     "paradis_sl_advect_bwd": (C.c_int, [C.POINTER(Geom), _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64,
                                         C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_float, _P, C.c_size_t, _P, _P]),
+    "paradis_sl_departure_coords": (C.c_int, [C.POINTER(Geom), _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                              C.c_float, C.c_int, C.c_int, _P]),
     "paradis_sl_host_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "paradis_sl_advect_fwd_bwd_host": (C.c_int, [C.POINTER(Geom), _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64,
                                                  C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, C.c_size_t]),

@@ -519,6 +519,7 @@ static int fill_params(Params& P, const paradis_sl_geom* g, int B, int V, float 
   P.dt = dt;
   P.Wm1 = (float)g->W - 1.0f; P.Hm1 = (float)g->H - 1.0f;
   P.Wpm1 = (float)(P.Wp - 1); P.Hpm1 = (float)(P.Hp - 1); P.pf = (float)p;
+  P.inv_Wpm1 = 1.0f / P.Wpm1; P.inv_Hpm1 = 1.0f / P.Hpm1;
   P.Ax = P.Wm1 / g->d_lon; P.Ay = P.Hm1 / g->d_lat;
   P.Cx = (float)((double)p - (double)g->min_lon * (double)P.Ax);
   P.Cy = (float)((double)p - (double)g->min_lat * (double)P.Ay);
@@ -857,6 +858,40 @@ extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* g
   else             rc = exact ? launch_bwd<true, 2>(P, vec, st, phases, cfl_cells, L, ws) : launch_bwd<false, 2>(P, vec, st, phases, cfl_cells, L, ws);
   if (rc) return rc;
   return check_launch("paradis_sl_advect_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity instrument: the departure-point chain alone
+// ---------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void departure_coords_kernel(const Params P, float* __restrict__ coords) {
+  const int c = blockIdx.y, b = blockIdx.z, pl = b * P.V + c;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P.ownN * P.W) return;
+  const int r = idx / P.W, x = idx - r * P.W, y = P.own0 + r;
+  const int aoff = (y - P.arr0) * P.W + x;
+  const float uu = plane_ptr_bc(P.u, P.u_sB, b, c, P.arrN, P.W)[aoff];
+  const float vv = plane_ptr_bc(P.v, P.v_sB, b, c, P.arrN, P.W)[aoff];
+  Traj t;
+  trajectory<EXACT>(P, uu, vv, __ldg(P.sin_lat + y), __ldg(P.cos_lat + y), __ldg(P.lon + x), t);
+  const long long plane = (long long)P.ownN * P.W;
+  float* o = coords + (long long)pl * 11 * plane + idx;
+  o[0] = t.ix; o[plane] = t.iy; o[2 * plane] = t.sa; o[3 * plane] = t.ca; o[4 * plane] = t.sb;
+  o[5 * plane] = t.cb; o[6 * plane] = t.s; o[7 * plane] = t.num; o[8 * plane] = t.den;
+  o[9 * plane] = t.lat; o[10 * plane] = t.lon;
+}
+
+extern "C" int paradis_sl_departure_coords(const paradis_sl_geom* geom, const float* u, const float* v, float* coords,
+                                           int B, int V, int64_t u_sB, int64_t v_sB, float dt, int interp, int math,
+                                           void* stream) {
+  Params P;
+  if (int rc = fill_params(P, geom, B, V, dt, interp, 0)) return rc;
+  if (!u || !v || !coords) return fail(PARADIS_ERR_NULL_POINTER, "NULL tensor pointer");
+  P.u = u; P.v = v; P.u_sB = u_sB; P.v_sB = v_sB;
+  dim3 grid((P.ownN * P.W + 255) / 256, V, B);
+  if (math == PARADIS_MATH_EXACT) departure_coords_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(P, coords);
+  else departure_coords_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(P, coords);
+  return check_launch("paradis_sl_departure_coords");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -399,3 +399,19 @@ class RawAdvection:
                                               self.ws_b.numel(), _ptr(self.status), _stream(field))
         _lib.check(rc, "paradis_sl_advect_bwd")
         return self.gfield, self.gu, self.gv
+
+
+def departure_coords(u: Tensor, v: Tensor, geometry: SLGeometry, dt: float, interpolation="bilinear",
+                     math="fast") -> Tensor:
+    """Parity instrument: [B, V, 11, H, W] = (ix, iy, sin lat', cos lat', sin lon', cos lon', sin_lat, num, den, lat, lon),
+    the intermediates of model/advection.py:82-94 and the sampler coordinates ATen floors."""
+    L = _lib.lib()
+    u, v = _inner_contig(u.float()), _inner_contig(v.float())
+    B, V, R, W = u.shape
+    out = torch.empty((B, V, 11, geometry.windows[3], W), dtype=torch.float32, device=u.device)
+    g = _geom_struct(geometry.tables, geometry.scalars, geometry.windows)
+    with torch.cuda.device(u.device):
+        rc = L.paradis_sl_departure_coords(C.byref(g), _ptr(u), _ptr(v), _ptr(out), B, V, u.stride(0), v.stride(0),
+                                           dt, _lib.INTERP[interpolation], _lib.MATH[math], _stream(u))
+    _lib.check(rc, "paradis_sl_departure_coords")
+    return out

@@ -380,3 +380,28 @@ def test_lat_band_nccl_two_gpus():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     assert '"scaling": "strong"' in res.stdout
+
+
+# ------------------------------------------------------------------ index mapping
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+@pytest.mark.parametrize("poles,H,W", [(False, 128, 256), (True, 721, 1440)])
+def test_exact_mode_coordinates_bit_identical_to_torch_cuda(poles, H, W, interp):
+    """EXACT mode replays the reference's fp32 operation order: every intermediate of
+    advection.py:82-96 and the sampler coordinates ATen floors are BIT-identical to the oracle's op
+    replay executed by torch on the same GPU, hence so is the stencil index of every point."""
+    from paradis_model_b200.ops import departure_coords
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, 1, 3, poles, DT)
+    latc, lonc, uc, vc = lat.cuda(), lon.cuda(), u.cuda(), v.cuda()
+    geo = P().SLGeometry.from_grids(latc, lonc)
+    G = O.Geometry(latc, lonc)
+    p = O.INTERP_PAD[interp]
+    lat_d, lon_d = O.departure_latlon(uc, vc, G, DT)
+    px, py = O.departure_pixels(uc, vc, G, DT)
+    _, _, ix, iy = O.sampler_coords(px, py, H, W, p)
+    got = departure_coords(uc, vc, geo, DT, interp, "exact")
+    assert torch.equal(got[:, :, 9], lat_d) and torch.equal(got[:, :, 10], lon_d)
+    assert torch.equal(got[:, :, 0], ix) and torch.equal(got[:, :, 1], iy)
+    fast = departure_coords(uc, vc, geo, DT, interp, "fast")
+    flips = ((fast[:, :, 0].floor() != ix.floor()) | (fast[:, :, 1].floor() != iy.floor())).float().mean().item()
+    assert flips < 2e-4                       # fast math: ~1 ulp of ix, isolated cell-edge flips only
+    assert (fast[:, :, 0] - ix).abs().max().item() < 1e-3 and (fast[:, :, 1] - iy).abs().max().item() < 1e-3
