@@ -247,6 +247,10 @@ _sl_advect.register_autograd(_sl_backward, setup_context=_sl_setup)
 
 
 DEFAULT_CFL_CELLS = 8.0
+# read once at import (not inside traced code): PARADIS_SL_MATH=fast|exact overrides the math mode,
+# PARADIS_SL_CHECK=1 synchronises after every call and raises on a device-side contract violation
+_ENV_MATH = os.environ.get("PARADIS_SL_MATH", "")
+_ENV_CHECK = os.environ.get("PARADIS_SL_CHECK") == "1"
 
 
 def sl_advect(field: Tensor, u: Tensor, v: Tensor, geometry: SLGeometry, dt: float,
@@ -261,12 +265,12 @@ def sl_advect(field: Tensor, u: Tensor, v: Tensor, geometry: SLGeometry, dt: flo
     are detected on the device and recomputed by the general path, results never depend on it;
     ``0`` disables the fused backward.
     """
-    if os.environ.get("PARADIS_SL_MATH"):
-        math = os.environ["PARADIS_SL_MATH"]
+    if _ENV_MATH:
+        math = _ENV_MATH
     out = torch.ops.paradis.sl_advect(field, u, v, geometry.tables, geometry.scalars, float(dt),
                                       _lib.INTERP[interpolation], bool(pole_fix), _lib.MATH[math],
                                       geometry.windows, float(cfl_cells))
-    if os.environ.get("PARADIS_SL_CHECK") == "1":
+    if _ENV_CHECK:
         check_status(field.device)
     return out
 

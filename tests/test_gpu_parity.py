@@ -405,3 +405,46 @@ def test_exact_mode_coordinates_bit_identical_to_torch_cuda(poles, H, W, interp)
     flips = ((fast[:, :, 0].floor() != ix.floor()) | (fast[:, :, 1].floor() != iy.floor())).float().mean().item()
     assert flips < 2e-4                       # fast math: ~1 ulp of ix, isolated cell-edge flips only
     assert (fast[:, :, 0] - ix).abs().max().item() < 1e-3 and (fast[:, :, 1] - iy).abs().max().item() < 1e-3
+
+
+# ------------------------------------------------------------------ framework integration
+def _small_problem(H=48, W=96, B=2, V=4):
+    lat, lon = O.make_grids(H, W, True)
+    field = O.smooth_field(lat, lon, B, V).float().cuda()
+    u, v = [t.float().cuda() for t in O.smooth_velocity(lat, lon, B, V, 1.5, DT)]
+    geo = P().SLGeometry.from_grids(lat.cuda(), lon.cuda())
+    return geo, field, u, v
+
+
+def test_torch_compile_fullgraph():
+    """trainer.py:261-267 compiles the model with fullgraph=True: the custom op must trace (fake
+    implementation + registered autograd) without a graph break."""
+    pkg = P()
+    geo, field, u, v = _small_problem()
+
+    def fn(f, uu, vv):
+        return pkg.sl_advect(f * 1.5, uu, vv, geo, DT, "bilinear").sin().sum()
+
+    f1, u1, v1 = [t.clone().requires_grad_(True) for t in (field, u, v)]
+    fn(f1, u1, v1).backward()
+    f2, u2, v2 = [t.clone().requires_grad_(True) for t in (field, u, v)]
+    cfn = torch.compile(fn, fullgraph=True, dynamic=False)
+    cfn(f2, u2, v2).backward()
+    assert relmax(f2.grad.cpu(), f1.grad.cpu()) < 1e-5
+    assert relmax(u2.grad.cpu(), u1.grad.cpu()) < 1e-5 and relmax(v2.grad.cpu(), v1.grad.cpu()) < 1e-5
+
+
+def test_bf16_autocast_and_checkpoint():
+    """train.py:56 runs bf16-mixed; paradis.py:63-70 wraps layers in non-reentrant checkpoints."""
+    from torch.utils.checkpoint import checkpoint
+    pkg = P()
+    geo, field, u, v = _small_problem()
+    f32 = pkg.sl_advect(field, u, v, geo, DT, "bicubic")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        fb, ub, vb = [t.bfloat16().requires_grad_(True) for t in (field, u, v)]
+        out = checkpoint(lambda a, b, c: pkg.sl_advect(a, b, c, geo, DT, "bicubic"), fb, ub, vb, use_reentrant=False)
+    assert out.dtype == torch.float32                       # as the reference's grid_sample under autocast
+    assert relmax(out.cpu(), f32.cpu()) < 3e-2              # bf16 inputs
+    out.sum().backward()
+    assert fb.grad.dtype == torch.bfloat16 and ub.grad.dtype == torch.bfloat16
+    assert torch.isfinite(fb.grad.float()).all() and torch.isfinite(ub.grad.float()).all()
