@@ -287,7 +287,8 @@ __global__ void plane_reach_kernel(const unsigned char* __restrict__ blkmax, int
 // data-independent order: deterministic, no atomics.
 // ---------------------------------------------------------------------------------------------
 constexpr int kGatherWarps = 8;
-constexpr int kQueue = 160;  // >= 31 + 128
+constexpr int kScan = 8;     // class bytes examined per lane and scan step
+constexpr int kQueue = 32 * kScan + 32;  // >= 31 left over + 32 * kScan new entries
 
 template <bool EXACT, int INTERP>
 __device__ __forceinline__ void gather_chunk(const Params& P, int pl, int Rd, int shift, float* acc,
@@ -392,29 +393,43 @@ __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const 
     for (int y = ylo; y <= yhi; ++y) {
       const signed char* crow = cls + (long long)(y - P.arr0) * P.W;
       const int cbase = Rd - (y + P.p) - OMIN;  // tap index a = cbase - class must be in [0, NT)
-      for (int x0 = 0; x0 < P.W; x0 += 128) {
-        const int x = x0 + lane * 4;
-        unsigned m4 = 0;
-        if (x + 3 < P.W && (P.W & 3) == 0) {
-          const char4 q = *reinterpret_cast<const char4*>(crow + x);
-          m4 |= ((unsigned)(cbase - q.x) < (unsigned)NT) ? 1u : 0u;
-          m4 |= ((unsigned)(cbase - q.y) < (unsigned)NT) ? 2u : 0u;
-          m4 |= ((unsigned)(cbase - q.z) < (unsigned)NT) ? 4u : 0u;
-          m4 |= ((unsigned)(cbase - q.w) < (unsigned)NT) ? 8u : 0u;
+      // byte patterns of the NT matching classes (0x80 = -128 is never stored: no match)
+      unsigned pat[NT];
+#pragma unroll
+      for (int a = 0; a < NT; ++a) {
+        const int cv = cbase - a;
+        pat[a] = ((cv >= -127 && cv <= 127) ? (unsigned)(cv & 0xff) : 0x80u) * 0x01010101u;
+      }
+      for (int x0 = 0; x0 < P.W; x0 += kScan * 32) {
+        const int x = x0 + lane * kScan;
+        unsigned m = 0;                      // bit k: candidate x + k matches
+        if (x + kScan - 1 < P.W && (P.W & (kScan - 1)) == 0) {
+          const uint2 q = *reinterpret_cast<const uint2*>(crow + x);
+          unsigned e0 = 0, e1 = 0;
+#pragma unroll
+          for (int a = 0; a < NT; ++a) { e0 |= __vcmpeq4(q.x, pat[a]); e1 |= __vcmpeq4(q.y, pat[a]); }
+          // one bit per byte: 0xFF bytes -> bits 0..3
+          m = (((e0 & 0x01010101u) * 0x01020408u) >> 24) | ((((e1 & 0x01010101u) * 0x01020408u) >> 24) << 4);
         } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (x + k < P.W && (unsigned)(cbase - crow[x + k]) < (unsigned)NT) m4 |= 1u << k;
+          for (int k = 0; k < kScan; ++k)
+            if (x + k < P.W && (unsigned)(cbase - crow[x + k]) < (unsigned)NT) m |= 1u << k;
         }
-        // raster-order compaction: position = matches in lower lanes + lower bits of own mask
-        const unsigned b0 = __ballot_sync(0xffffffffu, m4 & 1u), b1 = __ballot_sync(0xffffffffu, m4 & 2u);
-        const unsigned b2 = __ballot_sync(0xffffffffu, m4 & 4u), b3 = __ballot_sync(0xffffffffu, m4 & 8u);
-        const unsigned lt = (1u << lane) - 1u;
-        int pos = qn + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+        // raster-order compaction: exclusive prefix of the per-lane counts, then the lane's own bits in order
+        const int cnt = __popc(m);
+        int incl = cnt;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (m4 & (1u << k)) queue[pos++] = ((unsigned)y << 16) | (unsigned)(x + k);
-        qn += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        int pos = qn + incl - cnt;
+        while (m) {
+          const int k = __ffs(m) - 1;
+          m &= m - 1;
+          queue[pos++] = ((unsigned)y << 16) | (unsigned)(x + k);
+        }
+        qn += __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();
         int head = 0;
         while (qn - head >= 32) {
