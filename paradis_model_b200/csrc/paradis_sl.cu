@@ -290,8 +290,10 @@ constexpr int kGatherWarps = 8;
 constexpr int kScan = 8;     // class bytes examined per lane and scan step
 constexpr int kQueue = 32 * kScan + 32;  // >= 31 left over + 32 * kScan new entries
 
+struct GatherPlane { const float* __restrict__ u; const float* __restrict__ v; const float* __restrict__ g; float gm0, gm1; };
+
 template <bool EXACT, int INTERP>
-__device__ __forceinline__ void gather_chunk(const Params& P, int pl, int Rd, int shift, float* acc,
+__device__ __forceinline__ void gather_chunk(const Params& P, const GatherPlane& G, int Rd, int shift, float* acc,
                                              const unsigned* queue, int n, int lane) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
   float c[NT];
@@ -302,12 +304,13 @@ __device__ __forceinline__ void gather_chunk(const Params& P, int pl, int Rd, in
   if (lane < n) {
     const unsigned e = queue[lane];
     const int y = (int)(e >> 16), x = (int)(e & 0xffffu);  // global arrival row, column
-    const long long aoff = (long long)(y - P.arr0) * P.W + x;
-    const float uu = __ldg(plane_ptr(P.u, P.u_sB, P.V, P.arrN, P.W, pl) + aoff);
-    const float vv = __ldg(plane_ptr(P.v, P.v_sB, P.V, P.arrN, P.W, pl) + aoff);
-    float g;
-    if (P.pole_fix && (y == 0 || y == P.H - 1)) g = __ldg(P.gmean + 2 * pl + (y == 0 ? 0 : 1));
-    else g = __ldg(plane_ptr(P.gout, P.gout_sB, P.V, P.arrN, P.W, pl) + aoff);
+    const int aoff = (y - P.arr0) * P.W + x;
+    const float uu = __ldg(G.u + aoff), vv = __ldg(G.v + aoff);
+    float g = __ldg(G.g + aoff);
+    if (P.pole_fix) {                         // adjoint of the output pole mean
+      if (y == 0) g = G.gm0;
+      else if (y == P.H - 1) g = G.gm1;
+    }
     Traj t;
     trajectory<EXACT>(P, uu, vv, __ldg(P.sin_lat + y), __ldg(P.cos_lat + y), __ldg(P.lon + x), t);
     const float fx = floorf(t.ix), fy = floorf(t.iy);
@@ -379,6 +382,12 @@ __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const 
   __syncwarp();
   const int reach = P.plane_reach[pl];
   const signed char* cls = P.cls + (long long)pl * P.arrN * P.W;
+  GatherPlane G;
+  G.u = plane_ptr(P.u, P.u_sB, P.V, P.arrN, P.W, pl);
+  G.v = plane_ptr(P.v, P.v_sB, P.V, P.arrN, P.W, pl);
+  G.g = plane_ptr(P.gout, P.gout_sB, P.V, P.arrN, P.W, pl);
+  G.gm0 = G.gm1 = 0.0f;
+  if (P.pole_fix) { G.gm0 = __ldg(P.gmean + 2 * pl); G.gm1 = __ldg(P.gmean + 2 * pl + 1); }
 
   // destination rows (padded coordinates) folding onto r: itself, north cap, south cap
   for (int src = 0; src < 3; ++src) {
@@ -433,7 +442,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const 
         __syncwarp();
         int head = 0;
         while (qn - head >= 32) {
-          gather_chunk<EXACT, INTERP>(P, pl, Rd, shift, acc, queue + head, 32, lane);
+          gather_chunk<EXACT, INTERP>(P, G, Rd, shift, acc, queue + head, 32, lane);
           head += 32;
         }
         if (head) {  // move the tail (< 32 entries) to the front
@@ -447,7 +456,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const 
         }
       }
     }
-    if (qn) gather_chunk<EXACT, INTERP>(P, pl, Rd, shift, acc, queue, qn, lane);
+    if (qn) gather_chunk<EXACT, INTERP>(P, G, Rd, shift, acc, queue, qn, lane);
   }
   // adjoint of the first enforce_pole_continuity (advection.py:129): pole rows get their mean
   float* orow = P.gfield + ((long long)pl * P.ownN + (r - P.own0)) * P.W;
