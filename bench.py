@@ -39,7 +39,7 @@ CPU_SAMPLE_V = 8                                                # channels of th
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
@@ -281,7 +281,7 @@ def run_b200(args):
             "roofline": roofline,
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                               "bytes_per_unit": BYTES_STEP, "frac_of_8TBs": step_gbs / 8000.0},
-            "clocks": clocks, "gpu_launches": 16 * args.steps, "wall_ms_timed_region": wall_ms}
+            "clocks": clocks, "gpu_launches": 15 * args.steps, "wall_ms_timed_region": wall_ms}
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
