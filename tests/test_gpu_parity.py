@@ -448,3 +448,51 @@ def test_bf16_autocast_and_checkpoint():
     out.sum().backward()
     assert fb.grad.dtype == torch.bfloat16 and ub.grad.dtype == torch.bfloat16
     assert torch.isfinite(fb.grad.float()).all() and torch.isfinite(ub.grad.float()).all()
+
+
+# ------------------------------------------------------------------ ragged / degenerate shapes and error paths
+@pytest.mark.parametrize("H,W,poles", [(5, 6, True), (7, 18, False), (33, 50, True), (16, 1442, False)])
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+def test_ragged_shapes_scalar_paths(H, W, poles, interp):
+    """W not a multiple of 4 (no float4 path), W not a multiple of 8 (byte-wise class scan), tiny H:
+    forward and the general backward against the CPU oracle."""
+    if interp == "bicubic" and H < 6:
+        pytest.skip("padding 2 needs H >= 4 plus a row")
+    B, V = 2, 3
+    lat, lon = O.make_grids(H, W, poles)
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    field = torch.randn(B, V, H, W, generator=g)
+    sig = 1.2 * math.pi / H / DT
+    u = (torch.randn(B, V, H, W, generator=g) * sig).clamp_(-2 * sig, 2 * sig)
+    v = (torch.randn(B, V, H, W, generator=g) * sig).clamp_(-2 * sig, 2 * sig)
+    go = torch.randn(B, V, H, W, generator=g)
+    ref = O.sl_advect_fwd_bwd(field, u, v, lat, lon, DT, go, interp)
+    got = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, "exact")
+    # white noise against the CPU oracle: one ulp of ix at W = 1442 is 1.2e-4 cell, and EXACT follows
+    # torch-CUDA's scalar-divide semantics rather than the CPU kernel's (DESIGN.md section 7)
+    assert relmax(got[0], ref[0]) < 1e-3 and bad_fraction(got[0], ref[0], 1e-4) < 2e-2
+    assert relmax(got[1], ref[1]) < 1e-3 and bad_fraction(got[1], ref[1], 1e-4) < 2e-2
+    assert bad_fraction(got[2], ref[2], 1e-3) < 5e-3 and bad_fraction(got[3], ref[3], 1e-3) < 5e-3
+
+
+def test_error_paths_raise():
+    pkg = P()
+    lat, lon = O.make_grids(8, 16, True)
+    geo = pkg.SLGeometry.from_grids(lat.cuda(), lon.cuda())
+    x = torch.zeros(1, 2, 8, 16, device="cuda")
+    with pytest.raises(RuntimeError, match="shape mismatch"):
+        pkg.sl_advect(x[:, :, :7], x, x, geo, DT)
+    with pytest.raises(KeyError):
+        pkg.sl_advect(x, x, x, geo, DT, "nearest")
+    with pytest.raises(ValueError, match="separable"):
+        pkg.SLGeometry.from_grids(lat.cuda() + lon.cuda(), lon.cuda())
+    lat7, lon7 = O.make_grids(8, 16, True)
+    with pytest.raises(RuntimeError, match="even"):
+        g7 = pkg.SLGeometry(torch.zeros(2 * 8 + 15, device="cuda"), [0, 1, 0, 1], 8, 15)
+        y = torch.zeros(1, 1, 8, 15, device="cuda")
+        pkg.sl_advect(y, y, y, g7, DT)
+    # non-contiguous field (channel slice of a wider tensor) is accepted
+    wide = torch.randn(1, 4, 8, 16, device="cuda")
+    a = pkg.sl_advect(wide[:, 1:3], x, x, geo, DT)
+    b = pkg.sl_advect(wide[:, 1:3].contiguous(), x, x, geo, DT)
+    assert torch.equal(a, b)
