@@ -61,6 +61,12 @@ def lib():
     global _lib
     if _lib is None:
         path = os.environ.get("PARADIS_SL_LIB", LIB_PATH)
+        if not os.path.exists(path) and path == LIB_PATH:
+            try:                              # a fresh checkout: compile the CUDA sources once (nvcc, sm_100a)
+                from .build import build_library
+                build_library()
+            except Exception as exc:          # no nvcc: fail loudly below
+                build_error = exc
         if not os.path.exists(path):
             raise RuntimeError(
                 f"{path} is missing: build it with `python -m paradis_model_b200.build` "

@@ -808,6 +808,9 @@ static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_
   // ---- the caps (rows the sweep does not own): general path on row sub-windows, on side streams
   SideStreams* side = side_streams();
   if (side) cudaEventRecord(side->fork, st);
+  // the sweep goes first so that the (smaller) cap kernels fill the issue slots it leaves idle
+  const unsigned nblocks = (unsigned)((S.nbands * planes * S.nstrips + kSweepWarps - 1) / kSweepWarps);
+  kern<<<nblocks, kSweepWarps * 32, smem, st>>>(P, S);
   const int yh = rr + NT + 1;
   const int own_hi = P.own0 + P.ownN, arr_hi = P.arr0 + P.arrN;
   const int sub[2][2] = {{P.own0, lo}, {hi, own_hi}};
@@ -828,8 +831,6 @@ static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_
     if (int rc = launch_general<EXACT, INTERP>(Q, vec, cs, true, PARADIS_BWD_ALL, L.nblk)) return rc;
     if (side) cudaEventRecord(side->join[k], cs);
   }
-  const unsigned nblocks = (unsigned)((S.nbands * planes * S.nstrips + kSweepWarps - 1) / kSweepWarps);
-  kern<<<nblocks, kSweepWarps * 32, smem, st>>>(P, S);
   for (int k = 0; k < 2; ++k)
     if (forked[k]) cudaStreamWaitEvent(st, side->join[k], 0);
   // ---- planes that broke the contract are recomputed entirely by the general path

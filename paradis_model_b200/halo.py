@@ -157,10 +157,9 @@ def lat_band_advect(field, u, v, geometry, plan: BandPlan, dt: float, interpolat
 # ------------------------------------------------------------------------------------------
 def bench_latband(args, workload, rank, world, dev):
     import json
-    import time
     import paradis_model_b200 as P
     from . import synthetic as S
-    from bench import BYTES_STEP, CFL_CELLS, measured_peak
+    from bench import BYTES_STEP, CFL_CELLS, measured_peak   # only reached from bench.py --decomp latband
 
     H, W, V, Bg, poles = workload
     dt = S.DT_DEFAULT
