@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PARADIS_SL_ABI_VERSION 1
+#define PARADIS_SL_ABI_VERSION 2
 
 typedef enum paradis_status {
   PARADIS_OK = 0,
@@ -79,6 +79,15 @@ typedef struct paradis_sl_geom {
   int32_t own_row0, own_rows;
   int32_t arr_row0, arr_rows;
   int32_t fld_row0, fld_rows;
+  /* Optional peer halos of `field` (fused halo exchange over NVLink peer memory): instead of
+   * assembling the neighbours' boundary rows into `field`, pass pointers to them where they live
+   * (e.g. the neighbour GPUs' symmetric-memory outboxes, mapped into this process).  Each is
+   * [B*V, fld_peer_rows, W] and holds global rows [fld_row0 - fld_peer_rows, fld_row0) resp.
+   * [fld_row0 + fld_rows, fld_row0 + fld_rows + fld_peer_rows).  The kernels load stencil taps that
+   * fall there straight from the peer.  NULL / 0 when unused. */
+  const float* fld_peer_lo;
+  const float* fld_peer_hi;
+  int32_t fld_peer_rows;
 } paradis_sl_geom;
 
 int paradis_sl_abi_version(void);

@@ -26,7 +26,8 @@ class Geom(C.Structure):
                 ("min_lat", C.c_float), ("d_lat", C.c_float), ("min_lon", C.c_float), ("d_lon", C.c_float),
                 ("own_row0", C.c_int32), ("own_rows", C.c_int32),
                 ("arr_row0", C.c_int32), ("arr_rows", C.c_int32),
-                ("fld_row0", C.c_int32), ("fld_rows", C.c_int32)]
+                ("fld_row0", C.c_int32), ("fld_rows", C.c_int32),
+                ("fld_peer_lo", C.c_void_p), ("fld_peer_hi", C.c_void_p), ("fld_peer_rows", C.c_int32)]
 
 
 _lib = None
@@ -75,7 +76,7 @@ def lib():
         for name, (res, args) in _PROTOS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.paradis_sl_abi_version() != 1:
+        if handle.paradis_sl_abi_version() != 2:
             raise RuntimeError("libparadis_sl.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
     Traj t;
     trajectory<EXACT>(P, uu[k], vv[k], sp, cp, ll[k], t);
     float dx, dy;
-    stencil_eval<INTERP, false>(P, f, t, mean0, mean1, oo[k], dx, dy);
+    stencil_eval<INTERP, false>(P, f, pl, t, mean0, mean1, oo[k], dx, dy);
   }
   float* op = P.out + ((long long)pl * P.ownN + r) * P.W + x;
   if (VEC == 4) __stcs(reinterpret_cast<float4*>(op), *reinterpret_cast<float4*>(oo));
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
       cc[k] = (signed char)rc;
       if (own) {
         float val, dx, dy;
-        stencil_eval<INTERP, true>(P, f, t, mean0, mean1, val, dx, dy);
+        stencil_eval<INTERP, true>(P, f, pl, t, mean0, mean1, val, dx, dy);
         velocity_grads(P, t, sp, cp, gg[k] * dx, gg[k] * dy, ou[k], ov[k]);
       }
     }
@@ -537,6 +537,9 @@ static int fill_params(Params& P, const paradis_sl_geom* g, int B, int V, float 
   P.H = g->H; P.W = g->W; P.p = p; P.Hp = g->H + 2 * p; P.Wp = g->W + 2 * p; P.halfW = g->W / 2;
   P.own0 = g->own_row0; P.ownN = g->own_rows; P.arr0 = g->arr_row0; P.arrN = g->arr_rows;
   P.fld0 = g->fld_row0; P.fldN = g->fld_rows;
+  if (g->fld_peer_rows > 0 && (g->fld_peer_lo || g->fld_peer_hi)) {
+    P.f_lo = g->fld_peer_lo; P.f_hi = g->fld_peer_hi; P.f_halo = g->fld_peer_rows;
+  }
   P.it_own0 = P.own0; P.it_ownN = P.ownN; P.it_arr0 = P.arr0; P.it_arrN = P.arrN;
   P.sin_lat = g->sin_lat; P.cos_lat = g->cos_lat; P.lon = g->lon;
   P.min_lat = g->min_lat; P.d_lat = g->d_lat; P.min_lon = g->min_lon; P.d_lon = g->d_lon;

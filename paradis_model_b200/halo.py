@@ -10,9 +10,18 @@ the two latitude neighbours:
             grad_field rows with the deterministic inverse-stencil gather -- one exchange, no
             reverse add, bit-identical to the single-GPU result for the general path.
 
-The exchange is point-to-point (`torch.distributed.batch_isend_irecv`: NCCL send/recv over NVLink on
-GPUs, gloo in the CPU tests).  There is no collective on the data path.  The reference has no
-spatial decomposition at all (its only parallelism is DDP, train.py:49); this module is new.
+Two transports:
+
+* `exchange_rows`: point-to-point `torch.distributed.batch_isend_irecv` (NCCL send/recv over NVLink
+  on GPUs, gloo in the CPU tests) into an assembled [lo + rows + hi] tensor.
+* `PeerHalo` (field halos, GPUs only): every rank publishes its boundary rows in a symmetric-memory
+  outbox; the neighbours' outboxes are mapped into this process and their addresses are handed to
+  the kernels (`paradis_sl_geom.fld_peer_lo/hi`), which load the stencil taps that fall outside the
+  band straight from the peer GPU over NVLink -- the halo exchange is fused into the gather, nothing
+  is assembled or copied on the receiving side.
+
+There is no collective on the data path.  The reference has no spatial decomposition at all (its
+only parallelism is DDP, train.py:49); this module is new.
 """
 from __future__ import annotations
 
@@ -72,8 +81,8 @@ def make_plan(H: int, W: int, rank: int, world: int, cfl_cells: float, interpola
     bands = band_rows(H, world)
     row0, rows = bands[rank]
     halo = halo_rows(cfl_cells, interpolation)
-    if world > 1 and min(n for _, n in bands) < halo:
-        raise ValueError(f"bands of {min(n for _, n in bands)} rows are thinner than the halo ({halo} rows): "
+    if world > 1 and min(n for _, n in bands) <= halo:   # strictly thicker: a pole row is never in a neighbour's halo
+        raise ValueError(f"bands of {min(n for _, n in bands)} rows are not thicker than the halo ({halo} rows): "
                          "use fewer ranks or a smaller cfl_cells")
     lo = halo if rank > 0 else 0
     hi = halo if rank < world - 1 else 0
@@ -112,44 +121,88 @@ def exchange_rows(x: torch.Tensor, plan: BandPlan, group=None) -> torch.Tensor:
     return ext
 
 
+class PeerHalo:
+    """Boundary rows of `field` published in NVLink peer memory (torch symmetric memory).
+
+    outbox[0] = this band's first `halo` rows (read by the southern neighbour as ITS northern halo),
+    outbox[1] = this band's last `halo` rows (read by the northern neighbour as its southern halo).
+    `publish(field)` is stream-ordered: barrier (everybody finished reading the previous contents),
+    two small copies, barrier (everybody's rows are in place).  The kernels then dereference
+    `lo_ptr` / `hi_ptr` -- addresses inside the NEIGHBOURS' outboxes -- directly."""
+
+    def __init__(self, plan: BandPlan, B: int, V: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.plan, self.planes = plan, B * V
+        h, W = plan.halo, plan.W
+        self.box = symm.empty((2, B * V, h, W), dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.box, group=group if group is not None else dist.group.WORLD)
+        side_bytes = B * V * h * W * 4
+        ptrs = self.hdl.buffer_ptrs
+        self.lo_ptr = int(ptrs[plan.rank - 1]) + side_bytes if plan.rank > 0 else 0        # neighbour's last rows
+        self.hi_ptr = int(ptrs[plan.rank + 1]) if plan.rank < plan.world - 1 else 0       # neighbour's first rows
+
+    def publish(self, field: torch.Tensor) -> None:
+        h, W = self.plan.halo, self.plan.W
+        assert field.shape[2] == self.plan.rows and field.shape[0] * field.shape[1] == self.planes
+        self.hdl.barrier(channel=0)
+        self.box[0].copy_(field[:, :, :h].reshape(self.planes, h, W))
+        self.box[1].copy_(field[:, :, self.plan.rows - h:].reshape(self.planes, h, W))
+        self.hdl.barrier(channel=0)
+
+    def peer(self):
+        return (self.lo_ptr, self.hi_ptr, self.plan.halo)
+
+
 class _LatBandFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, field, u, v, geometry, plan, dt, interp, pole_fix, math, cfl, group):
+    def forward(ctx, field, u, v, geometry, plan, dt, interp, pole_fix, math, cfl, group, peer):
         from . import _lib
         own, ext = plan.windows()
-        f_ext = exchange_rows(field, plan, group)
-        g = geometry.band(own, own, ext)
-        out = torch.ops.paradis.sl_advect(f_ext, u, v, g.tables, g.scalars, dt, _lib.INTERP[interp], pole_fix,
+        if peer is not None:                 # field halo read in place from the neighbours (fused exchange)
+            field = field.contiguous()
+            peer.publish(field)
+            g = geometry.band(own, own, own, peer.peer())
+            f_saved = field
+        else:
+            f_saved = exchange_rows(field, plan, group)
+            g = geometry.band(own, own, ext)
+        out = torch.ops.paradis.sl_advect(f_saved, u, v, g.tables, g.scalars, dt, _lib.INTERP[interp], pole_fix,
                                           _lib.MATH[math], g.windows, cfl)
-        ctx.save_for_backward(f_ext, u, v)
-        ctx.meta = (geometry, plan, dt, interp, pole_fix, math, cfl, group)
+        ctx.save_for_backward(f_saved, u, v)
+        ctx.meta = (geometry, plan, dt, interp, pole_fix, math, cfl, group, peer)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         from . import _lib
-        f_ext, u, v = ctx.saved_tensors
-        geometry, plan, dt, interp, pole_fix, math, cfl, group = ctx.meta
+        f_saved, u, v = ctx.saved_tensors
+        geometry, plan, dt, interp, pole_fix, math, cfl, group, peer = ctx.meta
         own, ext = plan.windows()
         V = u.shape[1]
         packed = exchange_rows(torch.cat([grad_out.contiguous(), u, v], dim=1), plan, group)   # one message per side
         g_ext, u_ext, v_ext = packed[:, :V], packed[:, V:2 * V], packed[:, 2 * V:]
-        g = geometry.band(own, ext, ext)
-        gf, gu, gv = torch.ops.paradis.sl_advect_backward(g_ext, f_ext, u_ext, v_ext, g.tables, g.scalars, dt,
+        if peer is not None:
+            peer.publish(f_saved)            # the outbox may have been reused since forward
+            g = geometry.band(own, ext, own, peer.peer())
+        else:
+            g = geometry.band(own, ext, ext)
+        gf, gu, gv = torch.ops.paradis.sl_advect_backward(g_ext, f_saved, u_ext, v_ext, g.tables, g.scalars, dt,
                                                           _lib.INTERP[interp], pole_fix, _lib.MATH[math], g.windows,
                                                           cfl, True, True)
-        return gf, gu, gv, None, None, None, None, None, None, None, None
+        return gf, gu, gv, None, None, None, None, None, None, None, None, None
 
 
 def lat_band_advect(field, u, v, geometry, plan: BandPlan, dt: float, interpolation="bilinear", pole_fix=True,
-                    math="fast", cfl_cells: float = 8.0, group=None):
+                    math="fast", cfl_cells: float = 8.0, group=None, peer: Optional["PeerHalo"] = None):
     """sl_advect on this rank's latitude band: field, u, v, result are [B, V, plan.rows, W].
 
     `cfl_cells` sizes the halo (plan.halo must have been built with the same value): unlike the
     single-GPU call it is a CONTRACT here -- a departure stencil that leaves the halo sets the
-    device status word (paradis_model_b200.check_status raises DISPLACEMENT)."""
+    device status word (paradis_model_b200.check_status raises DISPLACEMENT).  With `peer` (a PeerHalo
+    built for the same plan and plane count) the field halo is not exchanged at all: the kernels read
+    the neighbours' boundary rows in place over NVLink."""
     return _LatBandFn.apply(field, u, v, geometry, plan, float(dt), interpolation, bool(pole_fix), math,
-                            float(cfl_cells), group)
+                            float(cfl_cells), group, peer)
 
 
 # ------------------------------------------------------------------------------------------
@@ -172,11 +225,18 @@ def bench_latband(args, workload, rank, world, dev):
     sl = slice(plan.row0, plan.row0 + plan.rows)
     field, u, v, go = [t[:, :, sl].contiguous().to(dev) for t in full]
     del full
+    peer, transport = None, "NCCL send/recv for field, grad_out, u, v"
+    if not getattr(args, "no_p2p", False):
+        try:
+            peer = PeerHalo(plan, Bg, V, dev)
+            transport = "field halo read in place over NVLink peer memory (symmetric memory); NCCL send/recv for grad_out|u|v"
+        except Exception as exc:   # symmetric memory unavailable: NCCL transport for everything
+            transport += f" (symmetric memory unavailable: {type(exc).__name__})"
 
     def step():
         f = field.requires_grad_(True)
         uu, vv = u.requires_grad_(True), v.requires_grad_(True)
-        out = lat_band_advect(f, uu, vv, geo, plan, dt, args.interp, True, args.math, CFL_CELLS)
+        out = lat_band_advect(f, uu, vv, geo, plan, dt, args.interp, True, args.math, CFL_CELLS, None, peer)
         out.backward(go)
         f.grad = uu.grad = vv.grad = None
 
@@ -206,8 +266,7 @@ def bench_latband(args, workload, rank, world, dev):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {H}x{W} mesh, V={V}, batch {Bg} GLOBAL, {args.interp}, "
                                    f"latitude bands x{world}, halo {plan.halo} rows",
-                       "parallelism": f"latband{world}: NCCL send/recv halo exchange, {halo_bytes} B per rank per "
-                                      f"forward (x3 in backward)"},
+                       "parallelism": f"latband{world}: {transport}; {halo_bytes} B of halo per rank per tensor"},
             "roofline_step": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
                               "frac": gbs / (peak * world), "peak_source": src}}), flush=True)
     dist.destroy_process_group()

@@ -85,7 +85,9 @@ class SLGeometry:
     sections padded to a multiple of 4 entries so every section is 16-byte aligned,
     ``scalars`` = [min_lat, d_lat, min_lon, d_lon] (fp32 values as python floats),
     ``windows`` = [H, W, own0, ownN, arr0, arrN, fld0, fldN] (latitude-band decomposition;
-    full mesh by default).
+    full mesh by default), optionally followed by [peer_lo_ptr, peer_hi_ptr, peer_rows]: device
+    addresses of the latitude neighbours' boundary rows of `field` (NVLink peer memory, see
+    include/paradis_sl.h) which the kernels then read in place instead of an assembled halo.
     """
 
     def __init__(self, tables: Tensor, scalars: List[float], H: int, W: int, windows=None):
@@ -119,10 +121,13 @@ class SLGeometry:
     def to(self, device) -> "SLGeometry":
         return SLGeometry(self.tables.to(device), self.scalars, self.H, self.W, self.windows)
 
-    def band(self, own: Tuple[int, int], arr: Tuple[int, int], fld: Tuple[int, int]) -> "SLGeometry":
-        """Same mesh, different row windows (row0, rows) for a latitude band."""
-        return SLGeometry(self.tables, self.scalars, self.H, self.W,
-                          [self.H, self.W, own[0], own[1], arr[0], arr[1], fld[0], fld[1]])
+    def band(self, own: Tuple[int, int], arr: Tuple[int, int], fld: Tuple[int, int], peer=None) -> "SLGeometry":
+        """Same mesh, different row windows (row0, rows) for a latitude band; ``peer`` =
+        (lo_ptr, hi_ptr, rows) for field halos read in place from the neighbours."""
+        w = [self.H, self.W, own[0], own[1], arr[0], arr[1], fld[0], fld[1]]
+        if peer is not None:
+            w += [int(peer[0]), int(peer[1]), int(peer[2])]
+        return SLGeometry(self.tables, self.scalars, self.H, self.W, w)
 
 
 def _geom_struct(tables: Tensor, scalars: List[float], windows: List[int]) -> _lib.Geom:
@@ -136,6 +141,8 @@ def _geom_struct(tables: Tensor, scalars: List[float], windows: List[int]) -> _l
     g.sin_lat, g.cos_lat, g.lon = base, base + 4 * Hp, base + 8 * Hp
     g.min_lat, g.d_lat, g.min_lon, g.d_lon = scalars
     g.own_row0, g.own_rows, g.arr_row0, g.arr_rows, g.fld_row0, g.fld_rows = [int(w) for w in windows[2:8]]
+    if len(windows) >= 11:
+        g.fld_peer_lo, g.fld_peer_hi, g.fld_peer_rows = (int(windows[8]) or None), (int(windows[9]) or None), int(windows[10])
     return g
 
 
@@ -144,7 +151,7 @@ def _check_inputs(field: Tensor, u: Tensor, v: Tensor, windows: List[int]):
         raise RuntimeError("paradis::sl_advect is a CUDA-only operator (no CPU fallback)")
     if field.dim() != 4 or u.shape != v.shape or u.dim() != 4:
         raise RuntimeError("paradis::sl_advect expects field [B,V,Rf,W] and u, v [B,V,Ra,W]")
-    H, W, own0, ownN, arr0, arrN, fld0, fldN = [int(w) for w in windows]
+    H, W, own0, ownN, arr0, arrN, fld0, fldN = [int(w) for w in windows[:8]]
     B, V = field.shape[:2]
     if tuple(field.shape) != (B, V, fldN, W) or tuple(u.shape) != (B, V, arrN, W):
         raise RuntimeError(f"paradis::sl_advect shape mismatch: field {tuple(field.shape)}, u {tuple(u.shape)}, "
@@ -379,7 +386,7 @@ class RawAdvection:
         self.interp, self.pole_fix, self.math = _lib.INTERP[interpolation], int(pole_fix), _lib.MATH[math]
         dev = geometry.tables.device
         L = _lib.lib()
-        H, W, own0, ownN, arr0, arrN, fld0, fldN = geometry.windows
+        H, W, own0, ownN, arr0, arrN, fld0, fldN = geometry.windows[:8]
         self.out = torch.empty((B, V, ownN, W), dtype=torch.float32, device=dev)
         self.gfield, self.gu, self.gv = [torch.empty_like(self.out) for _ in range(3)]
         self.ws_f = torch.empty(L.paradis_sl_advect_fwd_workspace(B, V), dtype=torch.uint8, device=dev)

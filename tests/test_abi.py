@@ -19,7 +19,7 @@ def header_functions():
 def test_library_builds_and_loads():
     path = build.build_library()
     assert os.path.exists(path)
-    assert _lib.lib().paradis_sl_abi_version() == 1
+    assert _lib.lib().paradis_sl_abi_version() == 2
 
 
 def test_exports_every_declared_symbol():
@@ -32,8 +32,8 @@ def test_exports_every_declared_symbol():
 
 
 def test_geom_struct_layout_matches_header():
-    # 2 x int32, 3 pointers, 4 floats, 6 x int32
-    assert C.sizeof(_lib.Geom) == 8 + 24 + 16 + 24
+    # 2 x int32, 3 pointers, 4 floats, 6 x int32, 2 pointers, int32
+    assert C.sizeof(_lib.Geom) == 8 + 24 + 16 + 24 + 16 + 8   # + 2 peer pointers, int32 + padding
 
 
 def test_argument_errors_without_gpu():

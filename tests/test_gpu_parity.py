@@ -496,3 +496,16 @@ def test_error_paths_raise():
     a = pkg.sl_advect(wide[:, 1:3], x, x, geo, DT)
     b = pkg.sl_advect(wide[:, 1:3].contiguous(), x, x, geo, DT)
     assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_peer_halo_matches_nccl_and_single_gpu():
+    """Latitude bands on 2 GPUs: the field halo read in place over NVLink peer memory (fused into the
+    gather) is bit-identical to the NCCL-assembled halo and to the single-GPU result."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29571", os.path.join(root, "tools", "check_p2p.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, (res.stdout[-1500:], res.stderr[-1500:])
+    assert res.stdout.count("p2p==nccl True; fwd==single-GPU True") == 2
