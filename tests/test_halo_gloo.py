@@ -32,11 +32,10 @@ def _worker(rank, world, port, H, W, cfl, interp, q):
         own = full[:, :, plan.row0:plan.row0 + plan.rows].contiguous()
         ext = halo.exchange_rows(own, plan)
         ok = torch.equal(ext, full[:, :, plan.ext_row0:plan.ext_row0 + plan.ext_rows])
-        # packed backward exchange
-        packed = torch.cat([own, own * 2, own * 3], dim=1)
-        pext = halo.exchange_rows(packed, plan)
+        # backward exchange: three tensors in one batch
+        a, b, c = halo.exchange_rows_multi([own, own * 2, own * 3], plan)
         ref = full[:, :, plan.ext_row0:plan.ext_row0 + plan.ext_rows]
-        ok = ok and torch.equal(pext, torch.cat([ref, ref * 2, ref * 3], dim=1))
+        ok = ok and torch.equal(a, ref) and torch.equal(b, ref * 2) and torch.equal(c, ref * 3)
         (own_w, ext_w) = plan.windows()
         ok = ok and own_w == (plan.row0, plan.rows) and ext_w[0] >= 0 and ext_w[0] + ext_w[1] <= H
         q.put((rank, bool(ok), plan.lo, plan.hi))
@@ -72,3 +71,10 @@ def test_band_rows_and_plan():
         halo.make_plan(32, 64, 0, 8, 6.0)
     single = halo.make_plan(32, 64, 0, 1, 6.0)
     assert single.ext_rows == 32
+    # cost-balanced bands: the ranks that own a polar cap get fewer rows, every row is owned once
+    cost = halo.row_costs(721, 1440, 6.0)
+    bands = halo.band_rows(721, 8, cost)
+    assert bands[0][0] == 0 and sum(n for _, n in bands) == 721
+    assert all(bands[k][0] + bands[k][1] == bands[k + 1][0] for k in range(7))
+    assert bands[0][1] < bands[3][1] and bands[7][1] < bands[4][1]
+    assert halo.make_plan(721, 1440, 0, 8, 6.0, balance=True).rows == bands[0][1]
