@@ -76,7 +76,7 @@ def lib():
         for name, (res, args) in _PROTOS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.paradis_sl_abi_version() != 2:
+        if handle.paradis_sl_abi_version() != 2 and not os.environ.get("PARADIS_SL_SKIP_ABI_CHECK"):
             raise RuntimeError("libparadis_sl.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -101,7 +102,7 @@ __global__ void pole_rows_fix_kernel(float* __restrict__ t, int rows, int row0, 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <bool EXACT, int INTERP, int VEC>
+template <bool EXACT, int INTERP, int VEC, bool PEER>
 __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
   const int c = blockIdx.y, b = blockIdx.z, pl = b * P.V + c;
   const unsigned unit = blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
     Traj t;
     trajectory<EXACT>(P, uu[k], vv[k], sp, cp, ll[k], t);
     float dx, dy;
-    stencil_eval<INTERP, false>(P, f, pl, t, mean0, mean1, oo[k], dx, dy);
+    stencil_eval<INTERP, false, PEER>(P, f, pl, t, mean0, mean1, oo[k], dx, dy);
   }
   float* op = P.out + ((long long)pl * P.ownN + r) * P.W + x;
   if (VEC == 4) __stcs(reinterpret_cast<float4*>(op), *reinterpret_cast<float4*>(oo));
@@ -165,7 +166,7 @@ __device__ __forceinline__ void velocity_grads(const Params& P, const Traj& t, f
 
 #include "sl_sweep.cuh"
 
-template <bool EXACT, int INTERP, int VEC>
+template <bool EXACT, int INTERP, int VEC, bool PEER>
 __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
   const int c = blockIdx.y, b = blockIdx.z, pl = b * P.V + c;
   if (P.plane_filter && !P.plane_filter[pl]) return;   // uniform per block
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
       cc[k] = (signed char)rc;
       if (own) {
         float val, dx, dy;
-        stencil_eval<INTERP, true>(P, f, pl, t, mean0, mean1, val, dx, dy);
+        stencil_eval<INTERP, true, PEER>(P, f, pl, t, mean0, mean1, val, dx, dy);
         velocity_grads(P, t, sp, cp, gg[k] * dx, gg[k] * dy, ou[k], ov[k]);
       }
     }
@@ -516,6 +517,16 @@ __global__ void geocyclic_pad_bwd_kernel(const float* __restrict__ gy, float* __
 // host side
 // ---------------------------------------------------------------------------------------------
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// Points per thread of the forward / arrival kernels.  4 consecutive columns (float4 rows, 4 independent
+// trajectories in flight) win for the 4-tap bilinear stencil (0.43 vs 0.59 ms at C3); the 16-tap bicubic
+// stencil is bound by its gathers and wants one point per lane -- consecutive lanes hit consecutive
+// addresses (few sectors per request) and 32 registers give full occupancy (0.97 vs 1.89 ms at C3).
+static int points_per_thread(int interp, bool vec_ok) {
+  static const int env = getenv("PARADIS_SL_VEC") ? atoi(getenv("PARADIS_SL_VEC")) : 0;   // experiments: 1 or 4
+  if (!vec_ok) return 1;
+  if (env == 1 || env == 4) return env;
+  return interp == PARADIS_INTERP_BICUBIC ? 1 : 4;
+}
 
 static int fill_params(Params& P, const paradis_sl_geom* g, int B, int V, float dt, int interp, int pole_fix) {
   if (!g) return fail(PARADIS_ERR_NULL_POINTER, "geom is NULL");
@@ -579,9 +590,16 @@ extern "C" size_t paradis_sl_advect_fwd_workspace(int B, int V) {
 
 template <bool EXACT, int INTERP>
 static void launch_fwd(const Params& P, int vec, dim3 grid, cudaStream_t st) {
-  if (vec == 4) sl_fwd_kernel<EXACT, INTERP, 4><<<grid, 256, 0, st>>>(P);
-  else sl_fwd_kernel<EXACT, INTERP, 1><<<grid, 256, 0, st>>>(P);
+  const bool peer = P.f_halo > 0;
+  if (vec == 4) {
+    if (peer) sl_fwd_kernel<EXACT, INTERP, 4, true><<<grid, 256, 0, st>>>(P);
+    else sl_fwd_kernel<EXACT, INTERP, 4, false><<<grid, 256, 0, st>>>(P);
+  } else {
+    if (peer) sl_fwd_kernel<EXACT, INTERP, 1, true><<<grid, 256, 0, st>>>(P);
+    else sl_fwd_kernel<EXACT, INTERP, 1, false><<<grid, 256, 0, st>>>(P);
+  }
 }
+
 
 extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* field, const float* u,
                                      const float* v, float* out, int B, int V, int64_t field_sB, int64_t u_sB,
@@ -605,7 +623,7 @@ extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* f
   }
   const bool vec_ok = (P.W % 4 == 0) && aligned16(field) && aligned16(u) && aligned16(v) && aligned16(out) &&
                       aligned16(P.lon) && (u_sB % 4 == 0) && (v_sB % 4 == 0);
-  const int vec = vec_ok ? 4 : 1;
+  const int vec = points_per_thread(interp, vec_ok);
   set_units(P, vec, P.ownN);
   const unsigned units = (unsigned)P.ownN * P.upr;
   dim3 grid((units + 255) / 256, V, B);
@@ -648,14 +666,21 @@ extern "C" size_t paradis_sl_advect_bwd_workspace(int B, int V, int arr_rows, in
 template <bool EXACT, int INTERP>
 static int launch_general(Params P, int vec, cudaStream_t st, bool want_field, int phases, int max_nblk) {
   const int planes = P.B * P.V;
+  vec = points_per_thread(INTERP, vec == 4);
   set_units(P, vec, P.it_arrN);
   const unsigned units = (unsigned)P.it_arrN * P.upr;
   dim3 grid((units + 255) / 256, P.V, P.B);
   if ((int)grid.x > max_nblk) return fail(PARADIS_ERR_WORKSPACE, "internal: blkmax layout");
   P.nblk = grid.x;
   if (phases & PARADIS_BWD_ARRIVAL) {
-    if (vec == 4) sl_bwd_arrival_kernel<EXACT, INTERP, 4><<<grid, 256, 0, st>>>(P);
-    else sl_bwd_arrival_kernel<EXACT, INTERP, 1><<<grid, 256, 0, st>>>(P);
+    const bool peer = P.f_halo > 0;
+    if (vec == 4) {
+      if (peer) sl_bwd_arrival_kernel<EXACT, INTERP, 4, true><<<grid, 256, 0, st>>>(P);
+      else sl_bwd_arrival_kernel<EXACT, INTERP, 4, false><<<grid, 256, 0, st>>>(P);
+    } else {
+      if (peer) sl_bwd_arrival_kernel<EXACT, INTERP, 1, true><<<grid, 256, 0, st>>>(P);
+      else sl_bwd_arrival_kernel<EXACT, INTERP, 1, false><<<grid, 256, 0, st>>>(P);
+    }
     if (want_field)
       plane_reach_kernel<<<(planes * 32 + 255) / 256, 256, 0, st>>>(P.blkmax, P.nblk, planes, P.plane_reach,
                                                                    P.plane_filter, P.plane_flag, P.reach_limit);
@@ -791,7 +816,7 @@ static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_
   constexpr int NT = Stencil<INTERP>::NT;
   SweepPlan S;
   memset(&S, 0, sizeof(S));
-  auto kern = sl_bwd_sweep_kernel<EXACT, INTERP>;
+  auto kern = P.f_halo > 0 ? sl_bwd_sweep_kernel<EXACT, INTERP, true> : sl_bwd_sweep_kernel<EXACT, INTERP, false>;
   const int rr = (int)ceil((double)cfl_cells);
   const int pitch = kSweepStrip + 2 * (NT - 1), cells = (2 * rr + NT) * pitch;
   const size_t smem = (size_t)kSweepWarps * (cells + (kTagRows * pitch + 3) / 4) * sizeof(float);
@@ -879,7 +904,7 @@ extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* g
   const bool vec_ok = (P.W % 4 == 0) && aligned16(field) && aligned16(u) && aligned16(v) && aligned16(grad_out) &&
                       aligned16(P.lon) && (!grad_u || (aligned16(grad_u) && aligned16(grad_v))) &&
                       (u_sB % 4 == 0) && (v_sB % 4 == 0) && (gout_sB % 4 == 0);
-  const int vec = vec_ok ? 4 : 1;
+  const int vec = vec_ok ? 4 : 1;   // float4 rows available (the sweep needs them); the arrival kernel picks its own
   const bool exact = math == PARADIS_MATH_EXACT;
   int rc;
   if (interp == 1) rc = exact ? launch_bwd<true, 1>(P, vec, st, phases, cfl_cells, L, ws) : launch_bwd<false, 1>(P, vec, st, phases, cfl_cells, L, ws);

@@ -97,7 +97,7 @@ template <int NT> struct StepOut {
 
 // Trajectory, contract check, (for own points) grad_u / grad_v, and the stencil weights of one
 // arrival point.  x: column (unwrapped, for the ring index), xw: wrapped column.
-template <bool EXACT, int INTERP, bool CORE>
+template <bool EXACT, int INTERP, bool CORE, bool PEER>
 __device__ __forceinline__ void sweep_compute(const Params& P, const SweepRow& R, const float* __restrict__ f,
                                               int pl, float mean0, float mean1, int ja, int wc, int ring, int pitch,
                                               int rr, int x, int xw, float uu, float vv, float g, float lonp, bool& violated,
@@ -119,7 +119,7 @@ __device__ __forceinline__ void sweep_compute(const Params& P, const SweepRow& R
 #ifndef PSL_DBG_NOGRADS
     if (R.gu_row) {
       float val, ddx, ddy;
-      stencil_eval<INTERP, true>(P, f, pl, t, mean0, mean1, val, ddx, ddy);
+      stencil_eval<INTERP, true, PEER>(P, f, pl, t, mean0, mean1, val, ddx, ddy);
       velocity_grads(P, t, R.sp, R.cp, g * ddx, g * ddy, ou, ov);
     }
 #endif
@@ -170,7 +170,7 @@ __device__ __forceinline__ void sweep_scatter(StepOut<NT>& o, float* acc, unsign
   }
 }
 
-template <bool EXACT, int INTERP>
+template <bool EXACT, int INTERP, bool PEER>
 __global__ void __launch_bounds__(kSweepWarps * 32) sl_bwd_sweep_kernel(const Params P, const SweepPlan S) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
   extern __shared__ float smem[];
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32) sl_bwd_sweep_kernel(const Pa
             *reinterpret_cast<float4*>(ll) = __ldg(reinterpret_cast<const float4*>(P.lon + x));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              sweep_compute<EXACT, INTERP, true>(P, R, f, pl, mean0, mean1, ja, wc, ring, pitch, rr, x + k, x + k, uu[k], vv[k],
+              sweep_compute<EXACT, INTERP, true, PEER>(P, R, f, pl, mean0, mean1, ja, wc, ring, pitch, rr, x + k, x + k, uu[k], vv[k],
                                                  gg[k], ll[k], violated, o[k], ou[k], ov[k]);
             if (R.gu_row) {
               __stcs(reinterpret_cast<float4*>(R.gu_row + x), *reinterpret_cast<float4*>(ou));
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32) sl_bwd_sweep_kernel(const Pa
           const int xa = ja + (ch << 5) + lane;
           if (xa < jb) {
             float ou = 0.0f, ov = 0.0f;
-            sweep_compute<EXACT, INTERP, true>(P, R, f, pl, mean0, mean1, ja, wc, ring, pitch, rr, xa, xa, __ldg(R.urow + xa),
+            sweep_compute<EXACT, INTERP, true, PEER>(P, R, f, pl, mean0, mean1, ja, wc, ring, pitch, rr, xa, xa, __ldg(R.urow + xa),
                                                __ldg(R.vrow + xa), __ldg(R.grow + xa), __ldg(P.lon + xa), violated, oa, ou,
                                                ov);
             if (R.gu_row) { __stcs(R.gu_row + xa, ou); __stcs(R.gv_row + xa, ov); }
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32) sl_bwd_sweep_kernel(const Pa
         if (xw < 0) xw += W; else if (xw >= W) xw -= W;
         if (h < 2 * R.hx) {
           float ou, ov;
-          sweep_compute<EXACT, INTERP, false>(P, R, f, pl, mean0, mean1, ja, wc, ring, pitch, rr, xa, xw, __ldg(R.urow + xw),
+          sweep_compute<EXACT, INTERP, false, PEER>(P, R, f, pl, mean0, mean1, ja, wc, ring, pitch, rr, xa, xw, __ldg(R.urow + xw),
                                               __ldg(R.vrow + xw), __ldg(R.grow + xw), __ldg(P.lon + xw), violated, oa, ou,
                                               ov);
         }
