@@ -666,7 +666,8 @@ extern "C" size_t paradis_sl_advect_bwd_workspace(int B, int V, int arr_rows, in
 template <bool EXACT, int INTERP>
 static int launch_general(Params P, int vec, cudaStream_t st, bool want_field, int phases, int max_nblk) {
   const int planes = P.B * P.V;
-  vec = points_per_thread(INTERP, vec == 4);
+  // the filtered (fallback) launch mostly consists of blocks that exit at once: keep their number small
+  vec = (P.plane_filter && vec == 4) ? 4 : points_per_thread(INTERP, vec == 4);
   set_units(P, vec, P.it_arrN);
   const unsigned units = (unsigned)P.it_arrN * P.upr;
   dim3 grid((units + 255) / 256, P.V, P.B);
