@@ -88,6 +88,14 @@ typedef struct paradis_sl_geom {
   const float* fld_peer_lo;
   const float* fld_peer_hi;
   int32_t fld_peer_rows;
+  /* Same for the arrival-window tensors of the backward, index 0 = u, 1 = v, 2 = grad_out.  When
+   * arr_peer_rows > 0 the three tensors hold only the rows of the arr window that are NOT covered by a
+   * non-NULL peer pointer: the first arr_peer_rows rows of the window are read from arr_peer_lo[k]
+   * (if non-NULL) and the last arr_peer_rows rows from arr_peer_hi[k], each [B*V, arr_peer_rows, W].
+   * With both sides present the tensors are [B, V, arr_rows - 2 * arr_peer_rows, W]. */
+  const float* arr_peer_lo[3];
+  const float* arr_peer_hi[3];
+  int32_t arr_peer_rows;
 } paradis_sl_geom;
 
 int paradis_sl_abi_version(void);

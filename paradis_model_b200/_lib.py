@@ -27,7 +27,8 @@ class Geom(C.Structure):
                 ("own_row0", C.c_int32), ("own_rows", C.c_int32),
                 ("arr_row0", C.c_int32), ("arr_rows", C.c_int32),
                 ("fld_row0", C.c_int32), ("fld_rows", C.c_int32),
-                ("fld_peer_lo", C.c_void_p), ("fld_peer_hi", C.c_void_p), ("fld_peer_rows", C.c_int32)]
+                ("fld_peer_lo", C.c_void_p), ("fld_peer_hi", C.c_void_p), ("fld_peer_rows", C.c_int32),
+                ("arr_peer_lo", C.c_void_p * 3), ("arr_peer_hi", C.c_void_p * 3), ("arr_peer_rows", C.c_int32)]
 
 
 _lib = None

@@ -112,9 +112,9 @@ __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
   const int y = P.own0 + (int)r;  // global arrival row
   const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
   const float* f = plane_ptr_bc(P.field, P.field_sB, b, c, P.fldN, P.W);
-  const int aoff = (y - P.arr0) * P.W + x;
-  const float* up = plane_ptr_bc(P.u, P.u_sB, b, c, P.arrN, P.W) + aoff;
-  const float* vp = plane_ptr_bc(P.v, P.v_sB, b, c, P.arrN, P.W) + aoff;
+  const int aoff = (y - P.uvg0) * P.W + x;
+  const float* up = plane_ptr_bc(P.u, P.u_sB, b, c, P.uvgN, P.W) + aoff;
+  const float* vp = plane_ptr_bc(P.v, P.v_sB, b, c, P.uvgN, P.W) + aoff;
   float mean0 = 0.0f, mean1 = 0.0f;
   if (P.pole_fix) { mean0 = __ldg(P.fmean + 2 * pl); mean1 = __ldg(P.fmean + 2 * pl + 1); }
   float uu[VEC], vv[VEC], ll[VEC], oo[VEC];
@@ -178,9 +178,8 @@ __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
     const int y = P.it_arr0 + (int)r;  // global arrival row
     const bool own = (y >= P.it_own0) && (y < P.it_own0 + P.it_ownN) && (P.gu != nullptr);
     const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
-    const int aoff = (y - P.arr0) * P.W + x;
-    const float* up = plane_ptr_bc(P.u, P.u_sB, b, c, P.arrN, P.W) + aoff;
-    const float* vp = plane_ptr_bc(P.v, P.v_sB, b, c, P.arrN, P.W) + aoff;
+    const float* up = arr_row<PEER>(P, plane_ptr_bc(P.u, P.u_sB, b, c, P.uvgN, P.W), 0, pl, y) + x;
+    const float* vp = arr_row<PEER>(P, plane_ptr_bc(P.v, P.v_sB, b, c, P.uvgN, P.W), 1, pl, y) + x;
     float uu[VEC], vv[VEC], ll[VEC], gg[VEC], ou[VEC], ov[VEC];
     signed char cc[VEC];
     if (VEC == 4) {
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
     float mean0 = 0.0f, mean1 = 0.0f;
     if (own) {
       f = plane_ptr_bc(P.field, P.field_sB, b, c, P.fldN, P.W);
-      const float* gp = plane_ptr_bc(P.gout, P.gout_sB, b, c, P.arrN, P.W) + aoff;
+      const float* gp = arr_row<PEER>(P, plane_ptr_bc(P.gout, P.gout_sB, b, c, P.uvgN, P.W), 2, pl, y) + x;
       if (VEC == 4) *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(gp));
       else {
 #pragma unroll
@@ -291,9 +290,9 @@ constexpr int kGatherWarps = 8;
 constexpr int kScan = 8;     // class bytes examined per lane and scan step
 constexpr int kQueue = 32 * kScan + 32;  // >= 31 left over + 32 * kScan new entries
 
-struct GatherPlane { const float* __restrict__ u; const float* __restrict__ v; const float* __restrict__ g; float gm0, gm1; };
+struct GatherPlane { const float* __restrict__ u; const float* __restrict__ v; const float* __restrict__ g; float gm0, gm1; int pl; };
 
-template <bool EXACT, int INTERP>
+template <bool EXACT, int INTERP, bool PEER>
 __device__ __forceinline__ void gather_chunk(const Params& P, const GatherPlane& G, int Rd, int shift, float* acc,
                                              const unsigned* queue, int n, int lane) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
@@ -305,9 +304,8 @@ __device__ __forceinline__ void gather_chunk(const Params& P, const GatherPlane&
   if (lane < n) {
     const unsigned e = queue[lane];
     const int y = (int)(e >> 16), x = (int)(e & 0xffffu);  // global arrival row, column
-    const int aoff = (y - P.arr0) * P.W + x;
-    const float uu = __ldg(G.u + aoff), vv = __ldg(G.v + aoff);
-    float g = __ldg(G.g + aoff);
+    const float uu = __ldg(arr_row<PEER>(P, G.u, 0, G.pl, y) + x), vv = __ldg(arr_row<PEER>(P, G.v, 1, G.pl, y) + x);
+    float g = __ldg(arr_row<PEER>(P, G.g, 2, G.pl, y) + x);
     if (P.pole_fix) {                         // adjoint of the output pole mean
       if (y == 0) g = G.gm0;
       else if (y == P.H - 1) g = G.gm1;
@@ -367,7 +365,7 @@ __device__ __forceinline__ void gather_chunk(const Params& P, const GatherPlane&
   }
 }
 
-template <bool EXACT, int INTERP>
+template <bool EXACT, int INTERP, bool PEER>
 __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const Params P) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
   extern __shared__ float smem[];
@@ -384,9 +382,10 @@ __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const 
   const int reach = P.plane_reach[pl];
   const signed char* cls = P.cls + (long long)pl * P.arrN * P.W;
   GatherPlane G;
-  G.u = plane_ptr(P.u, P.u_sB, P.V, P.arrN, P.W, pl);
-  G.v = plane_ptr(P.v, P.v_sB, P.V, P.arrN, P.W, pl);
-  G.g = plane_ptr(P.gout, P.gout_sB, P.V, P.arrN, P.W, pl);
+  G.pl = pl;
+  G.u = plane_ptr(P.u, P.u_sB, P.V, P.uvgN, P.W, pl);
+  G.v = plane_ptr(P.v, P.v_sB, P.V, P.uvgN, P.W, pl);
+  G.g = plane_ptr(P.gout, P.gout_sB, P.V, P.uvgN, P.W, pl);
   G.gm0 = G.gm1 = 0.0f;
   if (P.pole_fix) { G.gm0 = __ldg(P.gmean + 2 * pl); G.gm1 = __ldg(P.gmean + 2 * pl + 1); }
 
@@ -443,7 +442,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const 
         __syncwarp();
         int head = 0;
         while (qn - head >= 32) {
-          gather_chunk<EXACT, INTERP>(P, G, Rd, shift, acc, queue + head, 32, lane);
+          gather_chunk<EXACT, INTERP, PEER>(P, G, Rd, shift, acc, queue + head, 32, lane);
           head += 32;
         }
         if (head) {  // move the tail (< 32 entries) to the front
@@ -457,7 +456,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) sl_bwd_gather_kernel(const 
         }
       }
     }
-    if (qn) gather_chunk<EXACT, INTERP>(P, G, Rd, shift, acc, queue, qn, lane);
+    if (qn) gather_chunk<EXACT, INTERP, PEER>(P, G, Rd, shift, acc, queue, qn, lane);
   }
   // adjoint of the first enforce_pole_continuity (advection.py:129): pole rows get their mean
   float* orow = P.gfield + ((long long)pl * P.ownN + (r - P.own0)) * P.W;
@@ -552,6 +551,22 @@ static int fill_params(Params& P, const paradis_sl_geom* g, int B, int V, float 
     P.f_lo = g->fld_peer_lo; P.f_hi = g->fld_peer_hi; P.f_halo = g->fld_peer_rows;
   }
   P.it_own0 = P.own0; P.it_ownN = P.ownN; P.it_arr0 = P.arr0; P.it_arrN = P.arrN;
+  P.uvg0 = P.arr0; P.uvgN = P.arrN;
+  if (g->arr_peer_rows > 0) {
+    const int h = g->arr_peer_rows;
+    const bool lo = g->arr_peer_lo[0] != nullptr, hi = g->arr_peer_hi[0] != nullptr;
+    for (int k = 0; k < 3; ++k) {
+      if ((g->arr_peer_lo[k] != nullptr) != lo || (g->arr_peer_hi[k] != nullptr) != hi)
+        return fail(PARADIS_ERR_NULL_POINTER, "arr_peer_lo / arr_peer_hi must be given for u, v and grad_out alike");
+      P.a_lo[k] = g->arr_peer_lo[k]; P.a_hi[k] = g->arr_peer_hi[k];
+    }
+    if (lo || hi) {
+      P.a_halo = h;
+      P.uvg0 = P.arr0 + (lo ? h : 0);
+      P.uvgN = P.arrN - (lo ? h : 0) - (hi ? h : 0);
+      if (P.uvgN <= 0) return fail(PARADIS_ERR_BAD_SHAPE, "arr window smaller than its peer halos");
+    }
+  }
   P.sin_lat = g->sin_lat; P.cos_lat = g->cos_lat; P.lon = g->lon;
   P.min_lat = g->min_lat; P.d_lat = g->d_lat; P.min_lon = g->min_lon; P.d_lon = g->d_lon;
   P.dt = dt;
@@ -674,7 +689,7 @@ static int launch_general(Params P, int vec, cudaStream_t st, bool want_field, i
   if ((int)grid.x > max_nblk) return fail(PARADIS_ERR_WORKSPACE, "internal: blkmax layout");
   P.nblk = grid.x;
   if (phases & PARADIS_BWD_ARRIVAL) {
-    const bool peer = P.f_halo > 0;
+    const bool peer = P.f_halo > 0 || P.a_halo > 0;
     if (vec == 4) {
       if (peer) sl_bwd_arrival_kernel<EXACT, INTERP, 4, true><<<grid, 256, 0, st>>>(P);
       else sl_bwd_arrival_kernel<EXACT, INTERP, 4, false><<<grid, 256, 0, st>>>(P);
@@ -689,7 +704,7 @@ static int launch_general(Params P, int vec, cudaStream_t st, bool want_field, i
   if (!want_field || !(phases & PARADIS_BWD_GATHER)) return PARADIS_OK;
   const size_t smem = (size_t)kGatherWarps * (P.W + kQueue) * sizeof(float);
   if (smem > 227 * 1024) return fail(PARADIS_ERR_BAD_SHAPE, "W=%d too wide for the gather kernel's shared memory", P.W);
-  auto kern = sl_bwd_gather_kernel<EXACT, INTERP>;
+  auto kern = P.a_halo > 0 ? sl_bwd_gather_kernel<EXACT, INTERP, true> : sl_bwd_gather_kernel<EXACT, INTERP, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(PARADIS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   dim3 ggrid((P.it_ownN + kGatherWarps - 1) / kGatherWarps, planes);
@@ -817,7 +832,7 @@ static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_
   constexpr int NT = Stencil<INTERP>::NT;
   SweepPlan S;
   memset(&S, 0, sizeof(S));
-  auto kern = P.f_halo > 0 ? sl_bwd_sweep_kernel<EXACT, INTERP, true> : sl_bwd_sweep_kernel<EXACT, INTERP, false>;
+  auto kern = (P.f_halo > 0 || P.a_halo > 0) ? sl_bwd_sweep_kernel<EXACT, INTERP, true> : sl_bwd_sweep_kernel<EXACT, INTERP, false>;
   const int rr = (int)ceil((double)cfl_cells);
   const int pitch = kSweepStrip + 2 * (NT - 1), cells = (2 * rr + NT) * pitch;
   const size_t smem = (size_t)kSweepWarps * (cells + (kTagRows * pitch + 3) / 4) * sizeof(float);
@@ -900,7 +915,7 @@ extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* g
   if (pole_fix && (phases & PARADIS_BWD_ARRIVAL)) {
     const int warps = planes * 2;
     pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(field, field_sB, V, P.fldN, P.fld0, P.H, P.W, planes, fmean);
-    pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(grad_out, gout_sB, V, P.arrN, P.arr0, P.H, P.W, planes, gmean);
+    pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(grad_out, gout_sB, V, P.uvgN, P.uvg0, P.H, P.W, planes, gmean);
   }
   const bool vec_ok = (P.W % 4 == 0) && aligned16(field) && aligned16(u) && aligned16(v) && aligned16(grad_out) &&
                       aligned16(P.lon) && (!grad_u || (aligned16(grad_u) && aligned16(grad_v))) &&
@@ -923,9 +938,9 @@ __global__ void departure_coords_kernel(const Params P, float* __restrict__ coor
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P.ownN * P.W) return;
   const int r = idx / P.W, x = idx - r * P.W, y = P.own0 + r;
-  const int aoff = (y - P.arr0) * P.W + x;
-  const float uu = plane_ptr_bc(P.u, P.u_sB, b, c, P.arrN, P.W)[aoff];
-  const float vv = plane_ptr_bc(P.v, P.v_sB, b, c, P.arrN, P.W)[aoff];
+  const int aoff = (y - P.uvg0) * P.W + x;
+  const float uu = plane_ptr_bc(P.u, P.u_sB, b, c, P.uvgN, P.W)[aoff];
+  const float vv = plane_ptr_bc(P.v, P.v_sB, b, c, P.uvgN, P.W)[aoff];
   Traj t;
   trajectory<EXACT>(P, uu, vv, __ldg(P.sin_lat + y), __ldg(P.cos_lat + y), __ldg(P.lon + x), t);
   const long long plane = (long long)P.ownN * P.W;

@@ -191,9 +191,9 @@ __global__ void __launch_bounds__(kSweepWarps * 32) sl_bwd_sweep_kernel(const Pa
   for (int i = lane; i < cells; i += 32) acc[i] = 0.0f;
   __syncwarp();
 
-  const float* up = plane_ptr_bc(P.u, P.u_sB, b, c, P.arrN, P.W);
-  const float* vp = plane_ptr_bc(P.v, P.v_sB, b, c, P.arrN, P.W);
-  const float* gp = plane_ptr_bc(P.gout, P.gout_sB, b, c, P.arrN, P.W);
+  const float* up = plane_ptr_bc(P.u, P.u_sB, b, c, P.uvgN, P.W);
+  const float* vp = plane_ptr_bc(P.v, P.v_sB, b, c, P.uvgN, P.W);
+  const float* gp = plane_ptr_bc(P.gout, P.gout_sB, b, c, P.uvgN, P.W);
   const float* f = plane_ptr_bc(P.field, P.field_sB, b, c, P.fldN, P.W);
   float* gu_pl = P.gu ? P.gu + (long long)pl * S.outN * P.W : nullptr;
   float* gv_pl = P.gu ? P.gv + (long long)pl * S.outN * P.W : nullptr;
@@ -211,8 +211,9 @@ __global__ void __launch_bounds__(kSweepWarps * 32) sl_bwd_sweep_kernel(const Pa
     if (y >= arr_lo && y < arr_hi) {
       R.y = y;
       R.sp = __ldg(P.sin_lat + y); R.cp = __ldg(P.cos_lat + y);
-      const int rowoff = (y - arr_lo) * W;
-      R.urow = up + rowoff; R.vrow = vp + rowoff; R.grow = gp + rowoff;
+      R.urow = arr_row<PEER>(P, up, 0, pl, y);   // a neighbour's row when y lies in the peer halo
+      R.vrow = arr_row<PEER>(P, vp, 1, pl, y);
+      R.grow = arr_row<PEER>(P, gp, 2, pl, y);
       const bool core_row = (y >= ra) && (y < rb) && gu_pl;
       R.gu_row = core_row ? gu_pl + (y - S.out0) * W : nullptr;
       R.gv_row = core_row ? gv_pl + (y - S.out0) * W : nullptr;

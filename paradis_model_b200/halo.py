@@ -177,23 +177,41 @@ class PeerHalo:
         import torch.distributed._symmetric_memory as symm
         self.plan, self.planes = plan, B * V
         h, W = plan.halo, plan.W
-        self.box = symm.empty((2, B * V, h, W), dtype=torch.float32, device=device)
+        # slot 0: field; slots 1..3: u, v, grad_out of the backward.  [slot][side][plane][h][W]
+        self.box = symm.empty((4, 2, B * V, h, W), dtype=torch.float32, device=device)
         self.hdl = symm.rendezvous(self.box, group=group if group is not None else dist.group.WORLD)
         side_bytes = B * V * h * W * 4
         ptrs = self.hdl.buffer_ptrs
-        self.lo_ptr = int(ptrs[plan.rank - 1]) + side_bytes if plan.rank > 0 else 0        # neighbour's last rows
-        self.hi_ptr = int(ptrs[plan.rank + 1]) if plan.rank < plan.world - 1 else 0       # neighbour's first rows
+        south = int(ptrs[plan.rank - 1]) if plan.rank > 0 else 0
+        north = int(ptrs[plan.rank + 1]) if plan.rank < plan.world - 1 else 0
+        # my southern halo = the southern neighbour's LAST rows (its side 1); northern halo = side 0 of the northern one
+        self.lo = [south + (2 * k + 1) * side_bytes if south else 0 for k in range(4)]
+        self.hi = [north + (2 * k) * side_bytes if north else 0 for k in range(4)]
+        self.lo_ptr, self.hi_ptr = self.lo[0], self.hi[0]
+
+    def _put(self, slot: int, t: torch.Tensor) -> None:
+        h, W, n = self.plan.halo, self.plan.W, self.plan.rows
+        self.box[slot, 0].copy_(t[:, :, :h].reshape(self.planes, h, W))
+        self.box[slot, 1].copy_(t[:, :, n - h:].reshape(self.planes, h, W))
 
     def publish(self, field: torch.Tensor) -> None:
-        h, W = self.plan.halo, self.plan.W
         assert field.shape[2] == self.plan.rows and field.shape[0] * field.shape[1] == self.planes
         self.hdl.barrier(channel=0)
-        self.box[0].copy_(field[:, :, :h].reshape(self.planes, h, W))
-        self.box[1].copy_(field[:, :, self.plan.rows - h:].reshape(self.planes, h, W))
+        self._put(0, field)
+        self.hdl.barrier(channel=0)
+
+    def publish_backward(self, field: torch.Tensor, u: torch.Tensor, v: torch.Tensor, g: torch.Tensor) -> None:
+        """One barrier pair for all four tensors of the backward."""
+        self.hdl.barrier(channel=0)
+        for slot, t in enumerate((field, u, v, g)):
+            self._put(slot, t)
         self.hdl.barrier(channel=0)
 
     def peer(self):
         return (self.lo_ptr, self.hi_ptr, self.plan.halo)
+
+    def arr_peer(self):
+        return (self.lo[1:4], self.hi[1:4], self.plan.halo)
 
 
 class _LatBandFn(torch.autograd.Function):
@@ -221,11 +239,14 @@ class _LatBandFn(torch.autograd.Function):
         f_saved, u, v = ctx.saved_tensors
         geometry, plan, dt, interp, pole_fix, math, cfl, group, peer = ctx.meta
         own, ext = plan.windows()
-        g_ext, u_ext, v_ext = exchange_rows_multi([grad_out.contiguous(), u, v], plan, group)   # one NCCL group
         if peer is not None:
-            peer.publish(f_saved)            # the outbox may have been reused since forward
-            g = geometry.band(own, ext, own, peer.peer())
+            # nothing is exchanged or assembled: all four tensors keep their own rows, the kernels read the
+            # neighbours' boundary rows in place (the outboxes may have been reused since forward: republish)
+            g_ext, u_ext, v_ext = grad_out.contiguous(), u.contiguous(), v.contiguous()
+            peer.publish_backward(f_saved, u_ext, v_ext, g_ext)
+            g = geometry.band(own, ext, own, peer.peer(), peer.arr_peer())
         else:
+            g_ext, u_ext, v_ext = exchange_rows_multi([grad_out.contiguous(), u, v], plan, group)   # one NCCL group
             g = geometry.band(own, ext, ext)
         gf, gu, gv = torch.ops.paradis.sl_advect_backward(g_ext, f_saved, u_ext, v_ext, g.tables, g.scalars, dt,
                                                           _lib.INTERP[interp], pole_fix, _lib.MATH[math], g.windows,
@@ -270,7 +291,7 @@ def bench_latband(args, workload, rank, world, dev):
     if not getattr(args, "no_p2p", False):
         try:
             peer = PeerHalo(plan, Bg, V, dev)
-            transport = "field halo read in place over NVLink peer memory (symmetric memory); NCCL send/recv for grad_out|u|v"
+            transport = "all halos (field, grad_out, u, v) read in place over NVLink peer memory (symmetric memory), no NCCL on the data path"
         except Exception as exc:   # symmetric memory unavailable: NCCL transport for everything
             transport += f" (symmetric memory unavailable: {type(exc).__name__})"
 

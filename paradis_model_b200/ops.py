@@ -121,12 +121,16 @@ class SLGeometry:
     def to(self, device) -> "SLGeometry":
         return SLGeometry(self.tables.to(device), self.scalars, self.H, self.W, self.windows)
 
-    def band(self, own: Tuple[int, int], arr: Tuple[int, int], fld: Tuple[int, int], peer=None) -> "SLGeometry":
+    def band(self, own: Tuple[int, int], arr: Tuple[int, int], fld: Tuple[int, int], peer=None,
+             arr_peer=None) -> "SLGeometry":
         """Same mesh, different row windows (row0, rows) for a latitude band; ``peer`` =
-        (lo_ptr, hi_ptr, rows) for field halos read in place from the neighbours."""
+        (lo_ptr, hi_ptr, rows) for field halos read in place from the neighbours; ``arr_peer`` =
+        ([lo_u, lo_v, lo_g], [hi_u, hi_v, hi_g], rows) likewise for u, v, grad_out in the backward."""
         w = [self.H, self.W, own[0], own[1], arr[0], arr[1], fld[0], fld[1]]
-        if peer is not None:
-            w += [int(peer[0]), int(peer[1]), int(peer[2])]
+        if peer is not None or arr_peer is not None:
+            w += [int(peer[0]), int(peer[1]), int(peer[2])] if peer is not None else [0, 0, 0]
+        if arr_peer is not None:
+            w += [int(p) for p in arr_peer[0]] + [int(p) for p in arr_peer[1]] + [int(arr_peer[2])]
         return SLGeometry(self.tables, self.scalars, self.H, self.W, w)
 
 
@@ -143,7 +147,21 @@ def _geom_struct(tables: Tensor, scalars: List[float], windows: List[int]) -> _l
     g.own_row0, g.own_rows, g.arr_row0, g.arr_rows, g.fld_row0, g.fld_rows = [int(w) for w in windows[2:8]]
     if len(windows) >= 11:
         g.fld_peer_lo, g.fld_peer_hi, g.fld_peer_rows = (int(windows[8]) or None), (int(windows[9]) or None), int(windows[10])
+    if len(windows) >= 18:
+        for k in range(3):
+            g.arr_peer_lo[k] = int(windows[11 + k]) or None
+            g.arr_peer_hi[k] = int(windows[14 + k]) or None
+        g.arr_peer_rows = int(windows[17])
     return g
+
+
+def _held_arr_rows(windows: List[int]) -> int:
+    """Rows the u / v / grad_out tensors hold: the arr window minus the peer halos (if any)."""
+    n = int(windows[5])
+    if len(windows) >= 18 and int(windows[17]) > 0:
+        h = int(windows[17])
+        n -= (h if int(windows[11]) else 0) + (h if int(windows[14]) else 0)
+    return n
 
 
 def _check_inputs(field: Tensor, u: Tensor, v: Tensor, windows: List[int]):
@@ -153,7 +171,7 @@ def _check_inputs(field: Tensor, u: Tensor, v: Tensor, windows: List[int]):
         raise RuntimeError("paradis::sl_advect expects field [B,V,Rf,W] and u, v [B,V,Ra,W]")
     H, W, own0, ownN, arr0, arrN, fld0, fldN = [int(w) for w in windows[:8]]
     B, V = field.shape[:2]
-    if tuple(field.shape) != (B, V, fldN, W) or tuple(u.shape) != (B, V, arrN, W):
+    if tuple(field.shape) != (B, V, fldN, W) or tuple(u.shape) != (B, V, _held_arr_rows(windows), W):
         raise RuntimeError(f"paradis::sl_advect shape mismatch: field {tuple(field.shape)}, u {tuple(u.shape)}, "
                            f"windows {windows}")
     return B, V, H, W, ownN, arrN
@@ -200,8 +218,8 @@ def _sl_advect_backward(grad_out: Tensor, field: Tensor, u: Tensor, v: Tensor, t
     u = _inner_contig(u.float())
     v = _inner_contig(v.float())
     grad_out = _inner_contig(grad_out.float())
-    if tuple(grad_out.shape) != (B, V, arrN, W):
-        raise RuntimeError("paradis::sl_advect_backward: grad_out must cover the arrival window")
+    if tuple(grad_out.shape) != tuple(u.shape):
+        raise RuntimeError("paradis::sl_advect_backward: grad_out must cover the arrival window like u and v")
     gf = torch.empty((B, V, ownN, W), dtype=torch.float32, device=dev) if need_field else None
     gu = torch.empty((B, V, ownN, W), dtype=torch.float32, device=dev) if need_uv else None
     gv = torch.empty((B, V, ownN, W), dtype=torch.float32, device=dev) if need_uv else None

@@ -33,7 +33,7 @@ def test_exports_every_declared_symbol():
 
 def test_geom_struct_layout_matches_header():
     # 2 x int32, 3 pointers, 4 floats, 6 x int32, 2 pointers, int32
-    assert C.sizeof(_lib.Geom) == 8 + 24 + 16 + 24 + 16 + 8   # + 2 peer pointers, int32 + padding
+    assert C.sizeof(_lib.Geom) == 8 + 24 + 16 + 24 + 16 + 8 + 48 + 8   # + field peers, + 6 arrival peers, int32s + padding
 
 
 def test_argument_errors_without_gpu():
