@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
     ap.add_argument("--decomp", default="batch", choices=["batch", "latband"])
     ap.add_argument("--no-p2p", action="store_true", help="latband: NCCL transport for the field halo too")
+    ap.add_argument("--no-graph", action="store_true", help="latband: eager autograd step instead of a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()

@@ -302,6 +302,43 @@ def bench_latband(args, workload, rank, world, dev):
         out.backward(go)
         f.grad = uu.grad = vv.grad = None
 
+    mode = "eager autograd (torch.library op)"
+    if peer is not None and not getattr(args, "no_graph", False):
+        # The whole step -- publish, forward, publish, fused backward with its side streams and the
+        # symmetric-memory barriers -- is stream-ordered device work: capture it once in a CUDA graph and
+        # replay it, which removes the host launch overhead that dominates thin bands.
+        try:
+            from .ops import RawAdvection
+            own, ext = plan.windows()
+            Rf = RawAdvection(geo.band(own, own, own, peer.peer()), Bg, V, args.interp, True, args.math, CFL_CELLS)
+            Rb = RawAdvection(geo.band(own, ext, own, peer.peer(), peer.arr_peer()), Bg, V, args.interp, True,
+                              args.math, CFL_CELLS)
+
+            def raw_step():
+                peer.publish(field)
+                Rf.forward(field, u, v, dt)
+                peer.publish_backward(field, u, v, go)
+                Rb.backward(go, field, u, v, dt, 3)
+
+            for _ in range(3):
+                raw_step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                raw_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            dist.barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                raw_step()
+            step = graph.replay
+            mode = "one CUDA graph per step (C-ABI calls + symmetric-memory barriers captured)"
+        except Exception as exc:
+            mode += f" (graph capture unavailable: {type(exc).__name__}: {exc})"[:200]
+
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
@@ -329,7 +366,8 @@ def bench_latband(args, workload, rank, world, dev):
             "config": {"workload": f"{args.workload}: {H}x{W} mesh, V={V}, batch {Bg} GLOBAL, {args.interp}, "
                                    f"latitude bands x{world}, halo {plan.halo} rows",
                        "parallelism": f"latband{world} (cost-balanced bands, rank 0 owns {plan.rows} rows): {transport}; "
-                                      f"{halo_bytes} B of halo per rank per tensor"},
+                                      f"{halo_bytes} B of halo per rank per tensor",
+                       "launch": mode},
             "roofline_step": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
                               "frac": gbs / (peak * world), "peak_source": src}}), flush=True)
     dist.destroy_process_group()
