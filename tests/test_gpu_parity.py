@@ -544,3 +544,33 @@ def test_cuda_graph_capture_replays_bit_identically():
     torch.cuda.synchronize()
     for a, b in zip(ref, (R.out, R.gfield, R.gu, R.gv)):
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------ randomised robustness of the backward paths
+def test_random_shapes_sweep_vs_general_vs_oracle():
+    """40 random configurations (mesh size, pole layout, interpolation, displacement scale, cfl hint, windows):
+    fused sweep and general path must agree to rounding whatever the planner decides (bands, halos, caps,
+    fallback planes), and both must match the CPU oracle."""
+    import random
+    rng = random.Random(1234)
+    pkg = P()
+    for trial in range(40):
+        H = rng.choice([48, 61, 90, 128, 181, 240])
+        W = rng.choice([160, 192, 256, 360, 512])
+        poles = rng.random() < 0.5
+        interp = rng.choice(["bilinear", "bilinear", "bicubic"])
+        B, V = rng.choice([(1, 2), (2, 2), (1, 5)])
+        clip = rng.choice([0.5, 1.5, 3.0, 6.0])
+        cfl = rng.choice([1.0, 2.0, 4.0, 8.0, 12.0])          # sometimes too small: exercises the fallback
+        lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, poles, DT, seed=trial, cells_sigma=clip / 2,
+                                                   cells_clip=clip)
+        gen = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, cfl=0.0)
+        swp = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, cfl=cfl)
+        tag = f"trial {trial}: {H}x{W} poles={poles} {interp} B{B} V{V} clip={clip} cfl={cfl}"
+        assert torch.equal(gen[0], swp[0]), tag
+        assert relmax(swp[1], gen[1]) < 5e-6, tag
+        assert relmax(swp[2], gen[2]) < 1e-5 and relmax(swp[3], gen[3]) < 1e-5, tag
+        if trial % 4 == 0:
+            ref = O.sl_advect_fwd_bwd(field, u, v, lat, lon, DT, go, interp)
+            assert bad_fraction(swp[0], ref[0], 2e-4) < 5e-3, tag
+            assert bad_fraction(swp[1], ref[1], 2e-4) < 5e-3, tag
