@@ -109,6 +109,21 @@ int paradis_geocyclic_pad_fwd(const float* x, float* y, int64_t planes, int H, i
 int paradis_geocyclic_pad_bwd(const float* gy, float* gx, int64_t planes, int H, int W, int p,
                               void* stream);
 
+/* ---- Depthwise convolution with the GeoCyclic padding applied on the fly ------------------------
+ * Replaces `GeoCyclicPadding((k-1)/2)` + depthwise `nn.Conv2d(C, C, k, groups=C)` of SepConv
+ * (model/blocks.py:92-116) and of the static encoder (model/paradis.py:186-190) without materialising
+ * the padded tensor.  x, y, gy, gx: [B, C, H, W]; weight: [C, 1, k, k] (k = 3, 5 or 7); bias: [C] or NULL.
+ * All three are deterministic (no atomics).  bwd_weight needs caller scratch of
+ * paradis_geocyclic_dwconv_wgrad_workspace() bytes; gbias may be NULL. */
+int paradis_geocyclic_dwconv_fwd(const float* x, const float* weight, const float* bias, float* y, int B,
+                                 int C, int H, int W, int k, void* stream);
+int paradis_geocyclic_dwconv_bwd_input(const float* gy, const float* weight, float* gx, int B, int C,
+                                       int H, int W, int k, void* stream);
+size_t paradis_geocyclic_dwconv_wgrad_workspace(int B, int C, int H, int W, int k);
+int paradis_geocyclic_dwconv_bwd_weight(const float* x, const float* gy, float* gweight, float* gbias,
+                                        int B, int C, int H, int W, int k, void* workspace,
+                                        size_t workspace_bytes, void* stream);
+
 /* ---- Semi-Lagrangian advection core: model/advection.py:129-169 --------------------
  * (pole mean -> rotated-pole backtrack -> pixel coords -> GeoCyclic pad -> grid_sample
  *  -> pole mean), fused.

@@ -84,6 +84,13 @@ def geocyclic_pad_adjoint(g: torch.Tensor, p: int) -> torch.Tensor:
     return out.reshape(g.shape[0], g.shape[1], H, W)
 
 
+def geocyclic_depthwise(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
+    """First two lines of SepConv.forward (model/blocks.py:112-114): GeoCyclic pad by (k-1)//2, then the
+    depthwise k x k convolution (groups = channels, no conv padding)."""
+    k = weight.shape[-1]
+    return F.conv2d(geocyclic_pad(x, (k - 1) // 2), weight, bias, groups=x.shape[1])
+
+
 # --------------------------------------------------------------------------
 # Pole continuity (reference: model/advection.py:100-114)
 # --------------------------------------------------------------------------

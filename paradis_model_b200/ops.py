@@ -14,14 +14,14 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 from torch import Tensor
 
 from . import _lib
 
-__all__ = ["SLGeometry", "sl_advect", "geocyclic_pad", "check_status", "host_fwd_bwd"]
+__all__ = ["SLGeometry", "sl_advect", "geocyclic_pad", "geocyclic_dwconv", "check_status", "host_fwd_bwd"]
 
 _status_words: dict = {}
 
@@ -358,6 +358,79 @@ def geocyclic_pad(x: Tensor, pad_width: int) -> Tensor:
     assert x.dim() == 4, "Input must be 4-dimensional [batch, channels, lat, lon]"
     assert x.shape[3] % 2 == 0, "Number of longitude points must be even"
     return torch.ops.paradis.geocyclic_pad(x, int(pad_width))
+
+
+# --------------------------------------------------------------------------------------
+# geocyclic_dwconv: GeoCyclic padding fused into the depthwise convolution of SepConv (blocks.py:92-116)
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("paradis::geocyclic_dwconv", mutates_args=(), device_types="cuda")
+def _geocyclic_dwconv(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    B, Cn, H, W = x.shape
+    k = weight.shape[-1]
+    if tuple(weight.shape) != (Cn, 1, k, k):
+        raise RuntimeError("paradis::geocyclic_dwconv expects a depthwise weight [C, 1, k, k]")
+    xf, wf = x.float().contiguous(), weight.float().contiguous()
+    bf = bias.float().contiguous() if bias is not None else None
+    y = torch.empty_like(xf)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().paradis_geocyclic_dwconv_fwd(_ptr(xf), _ptr(wf), _ptr(bf), _ptr(y), B, Cn, H, W, k, _stream(x))
+    _lib.check(rc, "paradis_geocyclic_dwconv_fwd")
+    return y.to(x.dtype)
+
+
+@_geocyclic_dwconv.register_fake
+def _(x, weight, bias):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("paradis::geocyclic_dwconv_backward", mutates_args=(), device_types="cuda")
+def _geocyclic_dwconv_backward(gy: Tensor, x: Tensor, weight: Tensor, need_bias: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    B, Cn, H, W = x.shape
+    k = weight.shape[-1]
+    L = _lib.lib()
+    gyf, xf, wf = gy.float().contiguous(), x.float().contiguous(), weight.float().contiguous()
+    gx = torch.empty_like(xf)
+    gw = torch.empty_like(wf)
+    gb = torch.empty(Cn if need_bias else 0, dtype=torch.float32, device=x.device)
+    ws_bytes = L.paradis_geocyclic_dwconv_wgrad_workspace(B, Cn, H, W, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.paradis_geocyclic_dwconv_bwd_input(_ptr(gyf), _ptr(wf), _ptr(gx), B, Cn, H, W, k, _stream(x))
+        _lib.check(rc, "paradis_geocyclic_dwconv_bwd_input")
+        rc = L.paradis_geocyclic_dwconv_bwd_weight(_ptr(xf), _ptr(gyf), _ptr(gw), _ptr(gb) if need_bias else _ptr(None),
+                                                   B, Cn, H, W, k, _ptr(ws), ws_bytes, _stream(x))
+        _lib.check(rc, "paradis_geocyclic_dwconv_bwd_weight")
+    return gx, gw, gb
+
+
+@_geocyclic_dwconv_backward.register_fake
+def _(gy, x, weight, need_bias):
+    return torch.empty_like(x, dtype=torch.float32), torch.empty_like(weight, dtype=torch.float32), \
+        x.new_empty((x.shape[1] if need_bias else 0,), dtype=torch.float32)
+
+
+def _dw_setup(ctx, inputs, output):
+    x, weight, bias = inputs
+    ctx.save_for_backward(x, weight)
+    ctx.has_bias = bias is not None
+    ctx.dtypes = (x.dtype, weight.dtype, bias.dtype if bias is not None else None)
+
+
+def _dw_backward(ctx, gy):
+    x, weight = ctx.saved_tensors
+    gx, gw, gb = torch.ops.paradis.geocyclic_dwconv_backward(gy, x, weight, ctx.has_bias)
+    return gx.to(ctx.dtypes[0]), gw.to(ctx.dtypes[1]), (gb.to(ctx.dtypes[2]) if ctx.has_bias else None)
+
+
+_geocyclic_dwconv.register_autograd(_dw_backward, setup_context=_dw_setup)
+
+
+def geocyclic_dwconv(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """``depthwise_conv(GeoCyclicPadding((k-1)//2)(x))`` in one kernel (k = 3, 5, 7): drop-in for the first
+    two lines of SepConv.forward (model/blocks.py:112-114).  Differentiable w.r.t. x, weight and bias."""
+    assert x.dim() == 4, "Input must be 4-dimensional [batch, channels, lat, lon]"
+    assert x.shape[3] % 2 == 0, "Number of longitude points must be even"
+    return torch.ops.paradis.geocyclic_dwconv(x, weight, bias)
 
 
 # --------------------------------------------------------------------------------------

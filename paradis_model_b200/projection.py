@@ -36,6 +36,10 @@ class SepConv(nn.Module):
         self.pointwise = nn.Conv2d(input_dim, output_dim, kernel_size=1, bias=bias)
 
     def forward(self, x):
+        k = self.depthwise.kernel_size[0]
+        if x.is_cuda and k in (3, 5, 7) and self.depthwise.bias is None:
+            from .ops import geocyclic_dwconv     # padding fused into the depthwise convolution
+            return self.pointwise(geocyclic_dwconv(x, self.depthwise.weight))
         return self.pointwise(self.depthwise(self.geo_padding(x)))
 
 

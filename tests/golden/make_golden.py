@@ -79,9 +79,29 @@ def run_padding():
     print("padding_index", len(data) - 1, "maps")
 
 
+def run_sepconv():
+    """Reference SepConv (model/blocks.py:92-116), depthwise part: padded input -> depthwise conv."""
+    from model.blocks import SepConv  # reference
+    data = {"torch_version": torch.__version__}
+    g = torch.Generator().manual_seed(77)
+    for k in (3, 5, 7):
+        C, H, W = 3, 12, 16
+        m = SepConv(C, 4, (H, W), kernel_size=k)
+        x = torch.randn(2, C, H, W, generator=g, requires_grad=True)
+        y = m.depthwise(m.geo_padding(x))
+        gy = torch.randn(y.shape, generator=g)
+        y.backward(gy)
+        data[f"k{k}_x"] = x.detach().numpy(); data[f"k{k}_w"] = m.depthwise.weight.detach().numpy()
+        data[f"k{k}_y"] = y.detach().numpy(); data[f"k{k}_gy"] = gy.numpy()
+        data[f"k{k}_gx"] = x.grad.numpy(); data[f"k{k}_gw"] = m.depthwise.weight.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "sepconv_depthwise.npz"), **data)
+    print("sepconv_depthwise k=3,5,7")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     run_padding()
+    run_sepconv()
     for interp in ("bilinear", "bicubic"):
         tag = "bl" if interp == "bilinear" else "bc"
         run_case(f"adv_{tag}_poles_12x16_noise", 12, 16, 1, 2, True, interp, "noise", 1.5)

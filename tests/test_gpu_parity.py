@@ -574,3 +574,45 @@ def test_random_shapes_sweep_vs_general_vs_oracle():
             ref = O.sl_advect_fwd_bwd(field, u, v, lat, lon, DT, go, interp)
             assert bad_fraction(swp[0], ref[0], 2e-4) < 5e-3, tag
             assert bad_fraction(swp[1], ref[1], 2e-4) < 5e-3, tag
+
+
+# ------------------------------------------------------------------ GeoCyclic padding fused into the depthwise conv
+def test_dwconv_golden_from_reference_sepconv():
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "sepconv_depthwise.npz"))
+    pkg = P()
+    for k in (3, 5, 7):
+        x = torch.from_numpy(z[f"k{k}_x"]).cuda().requires_grad_(True)
+        w = torch.from_numpy(z[f"k{k}_w"]).cuda().requires_grad_(True)
+        y = pkg.geocyclic_dwconv(x, w)
+        y.backward(torch.from_numpy(z[f"k{k}_gy"]).cuda())
+        assert relmax(y.detach().cpu(), torch.from_numpy(z[f"k{k}_y"])) < 1e-5, k
+        assert relmax(x.grad.cpu(), torch.from_numpy(z[f"k{k}_gx"])) < 1e-5, k
+        assert relmax(w.grad.cpu(), torch.from_numpy(z[f"k{k}_gw"])) < 1e-5, k
+
+
+@pytest.mark.parametrize("k", [3, 5, 7])
+@pytest.mark.parametrize("shape", [(2, 5, 33, 64), (1, 3, 128, 256), (1, 2, 721, 1440), (3, 4, 9, 38)])
+def test_dwconv_vs_oracle(shape, k):
+    """fwd / grad input / grad weight / grad bias against pad + F.conv2d (blocks.py:112-114) on the CPU;
+    the backward is deterministic."""
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(k * 100 + H)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(C, 1, k, k, generator=g) / k
+    b = torch.randn(C, generator=g)
+    gy = torch.randn(B, C, H, W, generator=g)
+    xr, wr, br = [t.clone().requires_grad_(True) for t in (x, w, b)]
+    O.geocyclic_depthwise(xr, wr, br).backward(gy)
+    res = []
+    for _ in range(2):
+        xc, wc, bc = [t.cuda().requires_grad_(True) for t in (x, w, b)]
+        y = P().geocyclic_dwconv(xc, wc, bc)
+        y.backward(gy.cuda())
+        res.append((y.detach().cpu(), xc.grad.cpu(), wc.grad.cpu(), bc.grad.cpu()))
+    y_ref = O.geocyclic_depthwise(x, w, b)
+    assert relmax(res[0][0], y_ref) < 1e-5
+    assert relmax(res[0][1], xr.grad) < 1e-5
+    assert relmax(res[0][2], wr.grad) < 1e-4 and relmax(res[0][3], br.grad) < 1e-4
+    assert all(torch.equal(a, b2) for a, b2 in zip(res[0], res[1]))

@@ -119,3 +119,15 @@ def test_oracle_bitexact_vs_reference_module(interp):
     finally:
         sys.path.remove(REFERENCE)
         sys.path.remove(GOLDEN)
+
+
+def test_depthwise_oracle_matches_reference_sepconv_golden():
+    z = np.load(os.path.join(GOLDEN, "sepconv_depthwise.npz"))
+    for k in (3, 5, 7):
+        x = torch.from_numpy(z[f"k{k}_x"]).requires_grad_(True)
+        w = torch.from_numpy(z[f"k{k}_w"]).requires_grad_(True)
+        y = O.geocyclic_depthwise(x, w)
+        y.backward(torch.from_numpy(z[f"k{k}_gy"]))
+        assert relmax(y.detach(), torch.from_numpy(z[f"k{k}_y"])) < 1e-6
+        assert relmax(x.grad, torch.from_numpy(z[f"k{k}_gx"])) < 1e-5
+        assert relmax(w.grad, torch.from_numpy(z[f"k{k}_gw"])) < 1e-5
