@@ -94,6 +94,11 @@ def run_sepconv():
         data[f"k{k}_x"] = x.detach().numpy(); data[f"k{k}_w"] = m.depthwise.weight.detach().numpy()
         data[f"k{k}_y"] = y.detach().numpy(); data[f"k{k}_gy"] = gy.numpy()
         data[f"k{k}_gx"] = x.grad.numpy(); data[f"k{k}_gw"] = m.depthwise.weight.grad.numpy()
+    from model.blocks import PhysicalDownsample  # reference
+    for stride in (1, 2, 4):
+        x = torch.randn(2, 3, 17, 24, generator=g)
+        data[f"down_s{stride}_x"] = x.numpy()
+        data[f"down_s{stride}_y"] = PhysicalDownsample(stride=stride)(x).numpy()
     np.savez_compressed(os.path.join(HERE, "sepconv_depthwise.npz"), **data)
     print("sepconv_depthwise k=3,5,7")
 

@@ -616,3 +616,24 @@ def test_dwconv_vs_oracle(shape, k):
     assert relmax(res[0][1], xr.grad) < 1e-5
     assert relmax(res[0][2], wr.grad) < 1e-4 and relmax(res[0][3], br.grad) < 1e-4
     assert all(torch.equal(a, b2) for a, b2 in zip(res[0], res[1]))
+
+
+def test_blocks_drop_ins_match_reference_golden():
+    """paradis_model_b200.blocks.SepConv / PhysicalDownsample against outputs of the reference's classes."""
+    import os
+    from conftest import GOLDEN
+    from paradis_model_b200 import blocks
+    z = np.load(os.path.join(GOLDEN, "sepconv_depthwise.npz"))
+    for stride in (1, 2, 4):
+        x = torch.from_numpy(z[f"down_s{stride}_x"]).cuda()
+        y = blocks.PhysicalDownsample(stride=stride).cuda()(x)
+        ref = torch.from_numpy(z[f"down_s{stride}_y"])
+        assert y.shape == ref.shape and relmax(y.cpu(), ref) < 1e-5, stride
+    m = blocks.SepConv(3, 4, (12, 16), kernel_size=5).cuda()
+    assert sorted(m.state_dict()) == ["depthwise.weight", "pointwise.bias", "pointwise.weight"]
+    with torch.no_grad():
+        m.depthwise.weight.copy_(torch.from_numpy(z["k5_w"]))
+    x = torch.from_numpy(z["k5_x"]).cuda()
+    dw = P().geocyclic_dwconv(x, m.depthwise.weight)
+    assert relmax(dw.detach().cpu(), torch.from_numpy(z["k5_y"])) < 1e-5
+    assert m(x).shape == (2, 4, 12, 16)
