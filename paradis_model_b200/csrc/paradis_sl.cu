@@ -772,6 +772,9 @@ static bool plan_sweep(const Params& P, float cfl_cells, int planes, int capacit
   int nb = capacity_warps / (planes * nstrips);  // bands so that all tasks are resident at once
   if (nb < 1) nb = 1;
   while (nb > 1 && (hi - lo) / nb < 4 * yh) --nb;  // keep the row halo a minor cost
+#ifdef PSL_FORCE_NB
+  nb = PSL_FORCE_NB;
+#endif
   if (nb > kMaxBands) nb = kMaxBands;
   S.nbands = nb;
   {

@@ -22,7 +22,20 @@
 
 namespace psl {
 
-constexpr int kSweepWarps = 4;
+#ifndef PSL_SWEEP_WARPS
+#define PSL_SWEEP_WARPS 4
+#endif
+#if defined(PSL_SWEEP_MINB)
+#define PSL_SWEEP_BOUNDS __launch_bounds__(PSL_SWEEP_WARPS * 32, PSL_SWEEP_MINB)
+#elif defined(PSL_SWEEP_MAXREG)
+#define PSL_SWEEP_BOUNDS __maxnreg__(PSL_SWEEP_MAXREG)
+#else
+// 4 CTAs / SM for the 2x2 stencil (more resident warps measured slower: 2.19 -> 2.23 ms backward at 0.25 deg);
+// 6 CTAs / SM = 80 registers for 4x4, where a fourth row band of resident tasks pays for the few spills
+// (4.54 -> 3.98 ms)
+#define PSL_SWEEP_BOUNDS __launch_bounds__(PSL_SWEEP_WARPS * 32, INTERP == 2 ? 6 : 4)
+#endif
+constexpr int kSweepWarps = PSL_SWEEP_WARPS;
 constexpr int kMaxBands = 48;
 
 constexpr int kTagRows = 4;                   // clash tags cover (slot mod kTagRows, column)
@@ -171,7 +184,7 @@ __device__ __forceinline__ void sweep_scatter(StepOut<NT>& o, float* acc, unsign
 }
 
 template <bool EXACT, int INTERP, bool PEER>
-__global__ void __launch_bounds__(kSweepWarps * 32) sl_bwd_sweep_kernel(const Params P, const SweepPlan S) {
+__global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const SweepPlan S) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
