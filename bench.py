@@ -63,8 +63,11 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json)."""
+def ncu_traffic(kernel, captured_config):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json); None for any
+    configuration other than the one the capture was taken on (C3, bilinear)."""
+    if not captured_config:
+        return None
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         return json.load(open(path)).get(kernel)
@@ -267,7 +270,7 @@ def run_b200(args):
     dom = max(range(2), key=lambda i: phase[i])
     achieved = alg[dom] * pts_rank / (phase[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(names[dom]), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(names[dom], args.workload == "c3" and args.interp == "bilinear"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom] * pts_rank, "ms_per_launch": phase[dom],
                 "phases_ms": dict(zip(names, phase))}
     step_gbs = BYTES_STEP * pts_rank / (ms_step * 1e-3) / 1e9
