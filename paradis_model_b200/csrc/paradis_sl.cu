@@ -716,9 +716,12 @@ static int launch_general(Params P, int vec, cudaStream_t st, bool want_field, i
 // cfl_cells bounds the great-circle displacement |(u, v)| * dt in units of the latitude spacing.
 // From it: the row reach rr, and per arrival row the longitudinal reach in cells (it grows as
 // 1 / cos(lat), see halo_cells()).  Destination rows all of whose arrival rows have a reach of at
-// most kSweepMaxHalo are swept; they are cut into bands of equal cost, enough of them to fill the
+// most kSweepMaxHalo{2,4} are swept; they are cut into bands of equal cost, enough of them to fill the
 // GPU about once.
-constexpr int kSweepMaxHalo = 32;
+// Longest halo (cells either side of a strip) a swept row may need; rows poleward of it go to the general path.
+// Recomputing a wide halo costs the 2x2 stencil as much as the general path does (measured: 32 best), while the
+// general path visits every arrival point four times for the 4x4 stencil (96: 3.98 -> 3.83 ms backward).
+constexpr int kSweepMaxHalo2 = 32, kSweepMaxHalo4 = 96;
 constexpr int kSweepStrip = 128;
 
 template <int INTERP>
@@ -734,7 +737,7 @@ static bool plan_sweep(const Params& P, float cfl_cells, int planes, int capacit
   const int yh = rr + NT;                      // arrival rows either side that can reach a destination row
   S.reach.sin_delta = (float)sin(delta); S.reach.cos_delta = (float)cos(delta);
   S.reach.inv_dlam = (float)(1.0 / dlam); S.reach.extra = NT + 2;
-  S.reach.max_halo = kSweepMaxHalo;
+  S.reach.max_halo = NT == 2 ? kSweepMaxHalo2 : kSweepMaxHalo4;
   while (wc + 2 * (S.reach.max_halo + 16) > W && S.reach.max_halo > 16) S.reach.max_halo -= 16;
   if (wc + 2 * (S.reach.max_halo + 16) > W) return false;
   std::vector<int> need(H);

@@ -35,6 +35,9 @@ namespace psl {
 // (4.54 -> 3.98 ms)
 #define PSL_SWEEP_BOUNDS __launch_bounds__(PSL_SWEEP_WARPS * 32, INTERP == 2 ? 6 : 4)
 #endif
+#ifndef PSL_TOUCH_ON
+#define PSL_TOUCH_ON(NT) ((NT) == 2)      // the 4x4 kernel is register-bound at 80: touches cost it more than they save
+#endif
 constexpr int kSweepWarps = PSL_SWEEP_WARPS;
 constexpr int kMaxBands = 48;
 
@@ -220,7 +223,32 @@ __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const Sweep
   const int y_first = ra - (ring - 1) + rr - OMIN, y_last = rb - 1 + rr - OMIN;
   SweepRow R;
   R.head = 0;
+  // Warm-up loads ("touches"): while a row is processed, each lane loads one word of a 128-byte line the NEXT
+  // row step will need -- u, v, grad_out of the next arrival row and the field row that enters the stencil
+  // window with it -- over the columns [ja - 64, ja + 192).  The value is only consumed at the end of the row
+  // step, so the load never stalls; it replaces ~3.4k stall cycles per row on first-touch L2 / DRAM latency
+  // (`prefetch.global.L1` did not have that effect).  Measured 2.19 -> 2.07 ms backward at 0.25 deg.
+  constexpr bool kTouch = PSL_TOUCH_ON(NT);
+  const int pf_arr = lane >> 3;
+  int pf_col = ja - 64 + ((lane & 7) << 5);
+  if (pf_col < 0) pf_col += W; else if (pf_col >= W) pf_col -= W;
+  float pf_sink = 0.0f;
   for (int y = y_first; y <= y_last; ++y) {
+    float pf_val = 0.0f;
+    if (kTouch) {
+      const int yn = y + 1;
+      if (yn >= arr_lo && yn < arr_hi && yn <= y_last) {
+        const float* q = nullptr;
+        if (pf_arr == 0) q = arr_row<PEER>(P, up, 0, pl, yn);
+        else if (pf_arr == 1) q = arr_row<PEER>(P, vp, 1, pl, yn);
+        else if (pf_arr == 2) q = arr_row<PEER>(P, gp, 2, pl, yn);
+        else {
+          const int yf = yn + rr + NT - 1 + OMIN;   // last stencil row the next arrival row can reach
+          if (!PEER && yf >= P.fld0 && yf < P.fld0 + P.fldN) q = f + (long long)(yf - P.fld0) * W;
+        }
+        if (q) pf_val = __ldg(q + pf_col);
+      }
+    }
     if (y >= arr_lo && y < arr_hi) {
       R.y = y;
       R.sp = __ldg(P.sin_lat + y); R.cp = __ldg(P.cos_lat + y);
@@ -311,7 +339,9 @@ __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const Sweep
     for (int k = lane; k < pitch; k += 32) row[k] = 0.0f;
     __syncwarp();
     R.head = R.head + 1 == ring ? 0 : R.head + 1;
+    if (kTouch) pf_sink += pf_val;
   }
+  if (kTouch && pf_sink == 1.2345e-30f) violated = true;     // keeps the touches alive
   if (__any_sync(0xffffffffu, violated) && lane == 0) S.plane_flag[pl] = 1;
 }
 
