@@ -18,3 +18,12 @@ for (H, W, B, V, poles, cfl, interp) in [(96, 192, 1, 2, True, 3.0, "bilinear"),
     x = torch.randn(1, 2, H, W, device="cuda", requires_grad=True)
     P.geocyclic_pad(x, 2).sum().backward()
     print("case", H, W, interp, "ok", float(R.gfield.abs().sum()))
+
+# GeoCyclic padding fused into the depthwise convolution (forward, grad input, grad weight / bias)
+for (H, W, C, k) in [(33, 70, 3, 3), (40, 64, 2, 5), (17, 24, 2, 7)]:
+    x = torch.randn(2, C, H, W, device="cuda", requires_grad=True)
+    w = torch.randn(C, 1, k, k, device="cuda", requires_grad=True)
+    b = torch.randn(C, device="cuda", requires_grad=True)
+    P.geocyclic_dwconv(x, w, b).square().sum().backward()
+    torch.cuda.synchronize()
+    print("dwconv", H, W, k, "ok", float(x.grad.abs().sum()), float(w.grad.abs().sum()))
