@@ -113,7 +113,7 @@ template <int NT> struct StepOut {
 
 // Trajectory, contract check, (for own points) grad_u / grad_v, and the stencil weights of one
 // arrival point.  x: column (unwrapped, for the ring index), xw: wrapped column.
-template <bool EXACT, int INTERP, bool CORE, bool PEER>
+template <bool EXACT, int INTERP, bool CORE, bool PEER, bool SMALL = false>
 __device__ __forceinline__ void sweep_compute(const Params& P, const SweepRow& R, const float* __restrict__ f,
                                               int pl, float mean0, float mean1, int ja, int wc, int ring, int pitch,
                                               int rr, int x, int xw, float uu, float vv, float g, float lonp, bool& violated,
@@ -121,7 +121,7 @@ __device__ __forceinline__ void sweep_compute(const Params& P, const SweepRow& R
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
   o.key = -1; o.slot0 = 0; o.cidx = 0;
   Traj t;
-  trajectory<EXACT>(P, uu, vv, R.sp, R.cp, lonp, t);
+  trajectory<EXACT, SMALL>(P, uu, vv, R.sp, R.cp, lonp, t);
   const float fx = floorf(t.ix), fy = floorf(t.iy);
   const float tx = __fsub_rn(t.ix, fx), ty = __fsub_rn(t.iy, fy);
   const int x0 = (int)fx + OMIN;                 // padded column of tap 0
@@ -279,10 +279,19 @@ __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const Sweep
             *reinterpret_cast<float4*>(vv) = __ldg(reinterpret_cast<const float4*>(R.vrow + x));
             *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(R.grow + x));
             *reinterpret_cast<float4*>(ll) = __ldg(reinterpret_cast<const float4*>(P.lon + x));
+            // one range check for the lane's 8 backtrack angles instead of one per point (-1 % here; the same
+            // hoist costs the forward kernel registers and occupancy, so it is not used there)
+            if (!EXACT && small_angles<4>(P.dt, uu, vv)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              sweep_compute<EXACT, INTERP, true, PEER>(P, R, f, pl, mean0, mean1, ja, wc, ring, pitch, rr, x + k, x + k, uu[k], vv[k],
-                                                 gg[k], ll[k], violated, o[k], ou[k], ov[k]);
+              for (int k = 0; k < 4; ++k)
+                sweep_compute<EXACT, INTERP, true, PEER, true>(P, R, f, pl, mean0, mean1, ja, wc, ring, pitch, rr, x + k, x + k,
+                                                               uu[k], vv[k], gg[k], ll[k], violated, o[k], ou[k], ov[k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                sweep_compute<EXACT, INTERP, true, PEER>(P, R, f, pl, mean0, mean1, ja, wc, ring, pitch, rr, x + k, x + k, uu[k],
+                                                         vv[k], gg[k], ll[k], violated, o[k], ou[k], ov[k]);
+            }
             if (R.gu_row) {
               __stcs(reinterpret_cast<float4*>(R.gu_row + x), *reinterpret_cast<float4*>(ou));
               __stcs(reinterpret_cast<float4*>(R.gv_row + x), *reinterpret_cast<float4*>(ov));
