@@ -233,7 +233,14 @@ __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const Sweep
   int pf_col = ja - 64 + ((lane & 7) << 5);
   if (pf_col < 0) pf_col += W; else if (pf_col >= W) pf_col -= W;
   float pf_sink = 0.0f;
+  int hx_lane = 0;
   for (int y = y_first; y <= y_last; ++y) {
+    // the halo width is a function of the row only: lane l evaluates it for row y + l once every 32 rows
+    // (halo_cells costs ~40 instructions; evaluated per row by every lane it was 2 % of the kernel)
+    if (((y - y_first) & 31) == 0) {
+      const int yy = min(max(y + lane, arr_lo), arr_hi - 1);
+      hx_lane = halo_cells(S.reach, __ldg(P.sin_lat + yy), __ldg(P.cos_lat + yy));
+    }
     float pf_val = 0.0f;
     if (kTouch) {
       const int yn = y + 1;
@@ -258,7 +265,7 @@ __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const Sweep
       const bool core_row = (y >= ra) && (y < rb) && gu_pl;
       R.gu_row = core_row ? gu_pl + (y - S.out0) * W : nullptr;
       R.gv_row = core_row ? gv_pl + (y - S.out0) * W : nullptr;
-      int hx = halo_cells(S.reach, R.sp, R.cp);       // <= max_halo for every row a band may visit
+      int hx = __shfl_sync(0xffffffffu, hx_lane, (y - y_first) & 31);   // <= max_halo for every row a band may visit
       R.hx = min(hx, S.reach.max_halo + 16);          // (host/device rounding may differ by one step)
       const int nhalo = (2 * R.hx + 31) >> 5;
       if (NT == 2) {
