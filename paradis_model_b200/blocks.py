@@ -34,12 +34,13 @@ class PhysicalDownsample(nn.Module):
 
     def __init__(self, stride=4):
         super().__init__()
-        self.stride = stride
-        self.padding = GeoCyclicPadding(2)          # kept for structural parity with the reference
+        # both kept for structural parity with the reference (the fused kernel replaces them in forward)
+        self.pool = nn.AvgPool2d(kernel_size=5, stride=stride, count_include_pad=False)
+        self.padding = GeoCyclicPadding(2)
         self.register_buffer("_box", torch.full((1, 1, 5, 5), 1.0 / 25.0), persistent=False)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         C = x.shape[1]
         y = geocyclic_dwconv(x, self._box.expand(C, 1, 5, 5).contiguous())
-        s = self.stride
+        s = self.pool.stride if isinstance(self.pool.stride, int) else self.pool.stride[0]
         return y if s == 1 else y[:, :, ::s, ::s].contiguous()

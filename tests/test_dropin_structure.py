@@ -106,3 +106,26 @@ def test_standalone_projection_names_match_reference():
         _purge()
     assert sorted(mine.state_dict()) == sorted(ref.state_dict())
     assert all(mine.state_dict()[k].shape == ref.state_dict()[k].shape for k in ref.state_dict())
+
+
+def test_blocks_drop_ins_have_the_reference_signatures_and_parameters():
+    """paradis_model_b200.blocks.SepConv / PhysicalDownsample (optional third edit): same
+    constructor arguments, parameter names and shapes as model/blocks.py:57-116, so a reference state_dict loads."""
+    from paradis_model_b200 import blocks as mine
+    sys.path.insert(0, REFERENCE)
+    try:
+        _purge()
+        ref = importlib.import_module("model.blocks")
+        for k in (3, 5, 7):
+            a = ref.SepConv(6, 10, (16, 32), kernel_size=k, bias=True)
+            b = mine.SepConv(6, 10, (16, 32), kernel_size=k, bias=True)
+            assert list(a.state_dict()) == list(b.state_dict())
+            assert all(a.state_dict()[n].shape == b.state_dict()[n].shape for n in a.state_dict())
+            b.load_state_dict(a.state_dict(), strict=True)
+            assert b.geo_padding.pad_width == a.geo_padding.pad_width == (k - 1) // 2
+        a, b = ref.PhysicalDownsample(stride=4), mine.PhysicalDownsample(stride=4)
+        assert list(a.state_dict()) == list(b.state_dict()) == []
+        assert b.padding.pad_width == a.padding.pad_width == 2 and b.pool.stride == a.pool.stride == 4
+    finally:
+        sys.path.remove(REFERENCE)
+        _purge()
