@@ -790,7 +790,7 @@ static bool plan_sweep(const Params& P, float cfl_cells, int planes, int capacit
       S.rb[k] = (short)i;
     }
   }
-  S.nstrips = nstrips; S.wc = wc; S.rr = rr; S.ring = 2 * rr + NT; S.pitch = wc + 2 * (NT - 1);
+  S.nstrips = nstrips; S.wc = wc; S.rr = rr; S.ring = 2 * rr + NT; S.pitch = sweep_pitch(wc);
   S.planes = planes;
   return true;
 }
@@ -840,8 +840,7 @@ static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_
   memset(&S, 0, sizeof(S));
   auto kern = (P.f_halo > 0 || P.a_halo > 0) ? sl_bwd_sweep_kernel<EXACT, INTERP, true> : sl_bwd_sweep_kernel<EXACT, INTERP, false>;
   const int rr = (int)ceil((double)cfl_cells);
-  const int pitch = kSweepStrip + 2 * (NT - 1), cells = (2 * rr + NT) * pitch;
-  const size_t smem = (size_t)kSweepWarps * (cells + (kTagRows * pitch + 3) / 4) * sizeof(float);
+  const size_t smem = (size_t)kSweepWarps * sweep_warp_floats(2 * rr + NT, sweep_pitch(kSweepStrip)) * sizeof(float);
   int lo = -1, hi = -1, nsm = 148;
   bool ok = smem <= 200 * 1024;
   if (ok) ok = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
@@ -925,6 +924,7 @@ extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* g
   }
   const bool vec_ok = (P.W % 4 == 0) && aligned16(field) && aligned16(u) && aligned16(v) && aligned16(grad_out) &&
                       aligned16(P.lon) && (!grad_u || (aligned16(grad_u) && aligned16(grad_v))) &&
+                      (!grad_field || aligned16(grad_field)) &&   // the sweep retires rows with float4 stores
                       (u_sB % 4 == 0) && (v_sB % 4 == 0) && (gout_sB % 4 == 0);
   const int vec = vec_ok ? 4 : 1;   // float4 rows available (the sweep needs them); the arrival kernel picks its own
   const bool exact = math == PARADIS_MATH_EXACT;

@@ -42,6 +42,14 @@ constexpr int kSweepWarps = PSL_SWEEP_WARPS;
 constexpr int kMaxBands = 48;
 
 constexpr int kTagRows = 4;                   // clash tags cover (slot mod kTagRows, column)
+// Ring row layout: kRingLead margin columns, the strip's own wc columns (16-byte aligned, so that a finished row is
+// retired and cleared with float4 accesses), margin up to kRingPad columns in total.
+constexpr int kRingLead = 4, kRingPad = 8;
+__host__ __device__ constexpr int sweep_pitch(int wc) { return wc + kRingPad; }
+// floats per warp: ring + clash tags, rounded to 16 bytes
+__host__ __device__ constexpr int sweep_warp_floats(int ring, int pitch) {
+  return ring * pitch + (((kTagRows * pitch + 3) / 4 + 3) & ~3);
+}
 
 // Longitudinal reach (in cells, rounded up to 16) of an arrival row: the halo a strip needs on
 // either side.  |dlon| <= asin(sin(delta) / cos(|lat| + delta)) for a great-circle step delta.
@@ -55,7 +63,7 @@ __host__ __device__ __forceinline__ int halo_cells(const ReachModel& m, float si
 }
 
 struct SweepPlan {
-  int nbands, nstrips, wc, rr, ring, pitch;   // pitch = wc + 2 * (NT - 1)
+  int nbands, nstrips, wc, rr, ring, pitch;   // pitch = sweep_pitch(wc)
   int planes;
   ReachModel reach;
   short ra[kMaxBands], rb[kMaxBands];         // band k owns destination rows [ra[k], rb[k]); bands are
@@ -108,6 +116,7 @@ struct SweepRow {
 template <int NT> struct StepOut {
   int key;                         // ring cell of tap (0, 0), < 0: nothing to add
   int slot0, cidx;
+  int off1;                        // ring cell of tap (1, 0) (2x2 stencil: the scatter needs no slot arithmetic)
   float cc[NT * NT];
 };
 
@@ -119,7 +128,7 @@ __device__ __forceinline__ void sweep_compute(const Params& P, const SweepRow& R
                                               int rr, int x, int xw, float uu, float vv, float g, float lonp, bool& violated,
                                               StepOut<Stencil<INTERP>::NT>& o, float& ou, float& ov) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
-  o.key = -1; o.slot0 = 0; o.cidx = 0;
+  o.key = -1; o.slot0 = 0; o.cidx = 0; o.off1 = 0;
   Traj t;
   trajectory<EXACT, SMALL>(P, uu, vv, R.sp, R.cp, lonp, t);
   const float fx = floorf(t.ix), fy = floorf(t.iy);
@@ -140,8 +149,8 @@ __device__ __forceinline__ void sweep_compute(const Params& P, const SweepRow& R
     }
 #endif
   }
-  const int cidx = (x - ja) + dx + (NT - 1);     // ring column of tap 0
-  const bool hit = in_ring && (unsigned)cidx <= (unsigned)(wc + NT - 2);
+  const int cidx = (x - ja) + dx + kRingLead;    // ring column of tap 0
+  const bool hit = in_ring && (unsigned)(cidx - (kRingLead - NT + 1)) <= (unsigned)(wc + NT - 2);
   float wx[NT], wy[NT], d0[NT], d1[NT];
   axis_weights<INTERP, false>(tx, wx, d0);
   axis_weights<INTERP, false>(ty, wy, d1);
@@ -149,6 +158,12 @@ __device__ __forceinline__ void sweep_compute(const Params& P, const SweepRow& R
   if (slot0 >= ring) slot0 -= ring;
   o.slot0 = hit ? slot0 : 0; o.cidx = hit ? cidx : 0;
   o.key = hit ? slot0 * pitch + cidx : -1;
+  if (NT == 2) {
+    const int slot1 = slot0 + 1 == ring ? 0 : slot0 + 1;
+    o.off1 = hit ? slot1 * pitch + cidx : 0;
+  } else {
+    o.off1 = 0;
+  }
   const float gh = hit ? g : 0.0f;
 #pragma unroll
   for (int a = 0; a < NT; ++a) {
@@ -172,6 +187,19 @@ __device__ __forceinline__ void sweep_scatter(StepOut<NT>& o, float* acc, unsign
 #else
   resolve_clashes<NT>(o.key, (o.slot0 & (kTagRows - 1)) * pitch + o.cidx, tag, lane, o.cc, writer);
 #endif
+  if (NT == 2) {
+    float* r0 = acc + (writer ? o.key : 0);
+    float* r1 = acc + o.off1;
+    if (writer) r0[0] += o.cc[0];
+    __syncwarp();
+    if (writer) r0[1] += o.cc[1];
+    __syncwarp();
+    if (writer) r1[0] += o.cc[2];
+    __syncwarp();
+    if (writer) r1[1] += o.cc[3];
+    __syncwarp();
+    return;
+  }
   float* base = acc + o.cidx;
 #pragma unroll
   for (int a = 0; a < NT; ++a) {
@@ -189,7 +217,7 @@ __device__ __forceinline__ void sweep_scatter(StepOut<NT>& o, float* acc, unsign
 template <bool EXACT, int INTERP, bool PEER>
 __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const SweepPlan S) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1-D grid, most expensive bands first: task -> (band, plane, strip)
   const int task = blockIdx.x * kSweepWarps + warp;
@@ -202,7 +230,7 @@ __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const Sweep
   const int ja = strip * S.wc, jb = min(ja + S.wc, P.W), wc = jb - ja;
   const int ring = S.ring, pitch = S.pitch, rr = S.rr;
   const int cells = ring * pitch;
-  float* acc = smem + (size_t)warp * (cells + (kTagRows * pitch + 3) / 4);
+  float* acc = smem + (size_t)warp * sweep_warp_floats(ring, pitch);
   unsigned char* tag = reinterpret_cast<unsigned char*>(acc + cells);
   for (int i = lane; i < cells; i += 32) acc[i] = 0.0f;
   __syncwarp();
@@ -276,7 +304,7 @@ __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const Sweep
           StepOut<NT> o[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            o[k].key = -1; o[k].slot0 = 0; o[k].cidx = 0;
+            o[k].key = -1; o[k].slot0 = 0; o[k].cidx = 0; o[k].off1 = 0;
 #pragma unroll
             for (int t = 0; t < NT * NT; ++t) o[k].cc[t] = 0.0f;
           }
@@ -311,7 +339,7 @@ __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const Sweep
         // wide stencils: one point per lane and step (16 weights per point do not fit 4-fold in registers)
         for (int ch = 0; ch < ((wc + 31) >> 5); ++ch) {
           StepOut<NT> oa;
-          oa.key = -1; oa.slot0 = 0; oa.cidx = 0;
+          oa.key = -1; oa.slot0 = 0; oa.cidx = 0; oa.off1 = 0;
 #pragma unroll
           for (int t = 0; t < NT * NT; ++t) oa.cc[t] = 0.0f;
           const int xa = ja + (ch << 5) + lane;
@@ -328,7 +356,7 @@ __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const Sweep
       // halo columns: [ja - hx, ja) then [jb, jb + hx), one point per lane
       for (int ch = 0; ch < nhalo; ++ch) {
         StepOut<NT> oa;
-        oa.key = -1; oa.slot0 = 0; oa.cidx = 0;
+        oa.key = -1; oa.slot0 = 0; oa.cidx = 0; oa.off1 = 0;
 #pragma unroll
         for (int t = 0; t < NT * NT; ++t) oa.cc[t] = 0.0f;
         const int h = (ch << 5) + lane;
@@ -349,10 +377,11 @@ __global__ void PSL_SWEEP_BOUNDS sl_bwd_sweep_kernel(const Params P, const Sweep
     float* row = acc + R.head * pitch;
     if (i >= ra && i < rb) {
       float* orow = gf_pl + (i - S.out0) * W;
-      for (int k = lane; k < wc; k += 32) orow[k] = row[k + NT - 1];
+      for (int k = 4 * lane; k < wc; k += 128)
+        *reinterpret_cast<float4*>(orow + k) = *reinterpret_cast<const float4*>(row + kRingLead + k);
     }
     __syncwarp();
-    for (int k = lane; k < pitch; k += 32) row[k] = 0.0f;
+    for (int k = 4 * lane; k < pitch; k += 128) *reinterpret_cast<float4*>(row + k) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
     R.head = R.head + 1 == ring ? 0 : R.head + 1;
     if (kTouch) pf_sink += pf_val;
