@@ -131,7 +131,11 @@ int paradis_geocyclic_dwconv_bwd_weight(const float* x, const float* gy, float* 
  * *_sB = batch stride in elements (u and v may be views of one [B, 2V, H, W] tensor,
  * model/paradis.py:235-237); the inner three dims are contiguous.  out is contiguous.
  * `status` (optional) points to one device int32 that kernels set to a paradis_status
- * on a device-side contract violation. */
+ * on a device-side contract violation.
+ * Alignment: any float pointer is accepted.  The vectorised kernels (4 points per thread, and the
+ * fused backward sweep) are used when W % 4 == 0, every tensor pointer and the geometry tables are
+ * 16-byte aligned and the batch strides are multiples of 4 elements -- true for PyTorch allocations;
+ * otherwise the scalar forward and the general (two-kernel) backward run, with identical results. */
 size_t paradis_sl_advect_fwd_workspace(int B, int V);
 int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* field, const float* u,
                           const float* v, float* out, int B, int V, int64_t field_sB,
