@@ -135,7 +135,8 @@ int paradis_geocyclic_dwconv_bwd_weight(const float* x, const float* gy, float* 
  * Alignment: any float pointer is accepted.  The vectorised kernels (4 points per thread, and the
  * fused backward sweep) are used when W % 4 == 0, every tensor pointer and the geometry tables are
  * 16-byte aligned and the batch strides are multiples of 4 elements -- true for PyTorch allocations;
- * otherwise the scalar forward and the general (two-kernel) backward run, with identical results. */
+ * otherwise the scalar forward (bit-identical output) and the general two-kernel backward (same sums in a
+ * different, equally deterministic order) run. */
 size_t paradis_sl_advect_fwd_workspace(int B, int V);
 int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* field, const float* u,
                           const float* v, float* out, int B, int V, int64_t field_sB,
