@@ -17,6 +17,11 @@
 // Contract: |floor(iy) - row| <= rr and the longitudinal reach of a band <= its hx.  Every core
 // point checks it; a violation marks the plane in `plane_flag`, and the host always enqueues the
 // general (two-kernel) path behind the sweep, which recomputes exactly the flagged planes.
+//
+// What the kernel does about latency (it runs at 16 warps / SM, DESIGN.md section 8 has the measurements):
+// 4 points per lane in the core step (2x2 stencil); "touches" that pull the lines of the next row step into L1
+// one row ahead; no branch in `asin`, one range check for the 8 backtrack angles of a lane; the per-row halo
+// width computed once per 32 rows and shuffled; finished ring rows retired and cleared with float4 accesses.
 #pragma once
 #include "sl_device.cuh"
 
