@@ -71,3 +71,21 @@ def test_ops_fail_loudly_on_cpu():
         P.sl_advect(x, x, x, geo, 0.1)
     with pytest.raises((RuntimeError, NotImplementedError)):
         P.geocyclic_pad(x, 1)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU: one JSON line
+    with the same metric / unit / config as the product arm plus impl, cpu_baseline and a zero-copy e2e object."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--workload", "c2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "grid-pt*ch/s" and line["higher_is_better"] is True
+    assert line["metric"] == "SL advection fwd+bwd grid-pts*ch/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and line["n_gpus"] == 1 and line["vs_baseline"] is None
