@@ -13,6 +13,7 @@ from .build import LIB_PATH
 OK = 0
 INTERP = {"bilinear": 1, "bicubic": 2}
 MATH = {"fast": 0, "exact": 1}
+MAX_DISP_ROWS = 126   # PARADIS_SL_MAX_DISP_ROWS
 STATUS_NAMES = {
     0: "OK", 1: "BAD_SHAPE", 2: "ODD_WIDTH", 3: "BAD_INTERP", 4: "NULL_POINTER", 5: "WORKSPACE",
     6: "CUDA", 7: "DISPLACEMENT", 8: "NO_DEVICE",
@@ -68,6 +69,7 @@ def lib():
     global _lib
     if _lib is None:
         path = os.environ.get("PARADIS_SL_LIB", LIB_PATH)
+        build_error = None
         if not os.path.exists(path) and path == LIB_PATH:
             try:                              # a fresh checkout: compile the CUDA sources once (nvcc, sm_100a)
                 from .build import build_library
@@ -77,7 +79,8 @@ def lib():
         if not os.path.exists(path):
             raise RuntimeError(
                 f"{path} is missing: build it with `python -m paradis_model_b200.build` "
-                "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this operator.")
+                "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this operator."
+                + (f"\nThe automatic build failed: {build_error}" if build_error is not None else ""))
         handle = C.CDLL(path)
         for name, (res, args) in _PROTOS.items():
             fn = getattr(handle, name)

@@ -144,27 +144,8 @@ __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
 // ---------------------------------------------------------------------------------------------
 // backward, per arrival point: grad_u, grad_v and the row class of the departure cell
 // ---------------------------------------------------------------------------------------------
-// Jacobian of (ix, iy) w.r.t. (u, v): closed form of SURVEY 8a, validated in oracle/sl_oracle.py
-__device__ __forceinline__ void velocity_grads(const Params& P, const Traj& t, float sp, float cp, float gix,
-                                               float giy, float& gu, float& gv) {
-  const float r2 = fmaf(t.num, t.num, t.den * t.den);
-  float inv_r2;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_r2) : "f"(r2));
-  inv_r2 = r2 > 0.0f ? inv_r2 : 0.0f;
-  const float cacb = t.ca * t.cb, casb = t.ca * t.sb, sasb = t.sa * t.sb, sacb = t.sa * t.cb;
-  const float dlam_db = (t.den * cacb + t.num * casb * cp) * inv_r2;
-  const float dlam_da = (-t.den * sasb + t.num * fmaf(sacb, cp, t.ca * sp)) * inv_r2;
-  const bool inside = (t.s >= P.clamp_lo) && (t.s <= P.clamp_hi);
-  const float sc = fminf(fmaxf(t.s, P.clamp_lo), P.clamp_hi);
-  const float dphi_ds = inside ? rsqrtf(fmaf(-sc, sc, 1.0f)) : 0.0f;
-  const float ds_db = -casb * sp;
-  const float ds_da = fmaf(t.ca, cp, -sacb * sp);
-  const float kx = gix * P.Ax, ky = giy * P.Ay * dphi_ds;
-  gu = -P.dt * fmaf(kx, dlam_db, ky * ds_db);
-  gv = -P.dt * fmaf(kx, dlam_da, ky * ds_da);
-}
-
 #include "sl_sweep.cuh"
+#include "sl_rows.cuh"
 
 template <bool EXACT, int INTERP, int VEC, bool PEER>
 __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
@@ -224,7 +205,7 @@ __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
       if (own) {
         float val, dx, dy;
         stencil_eval<INTERP, true, PEER>(P, f, pl, t, mean0, mean1, val, dx, dy);
-        velocity_grads(P, t, sp, cp, gg[k] * dx, gg[k] * dy, ou[k], ov[k]);
+        velocity_grads<EXACT>(P, t, sp, cp, gg[k] * dx, gg[k] * dy, ou[k], ov[k]);
       }
     }
     if (P.cls) {
@@ -652,9 +633,9 @@ extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* f
   return check_launch("paradis_sl_advect_fwd");
 }
 
-// workspace layout (backward): fmean | gmean | plane_reach[3] | plane_flag | blkmax[3] | cls
+// workspace layout (backward): fmean | gmean | plane_reach[3] | plane_flag | hx | blkmax[3] | cls
 // (three reach / blkmax sets: the two polar caps run concurrently with the sweep, then the fallback)
-struct BwdWs { size_t fmean, gmean, reach, reach_stride, flag, blkmax, blkmax_stride, cls, total; int nblk; };
+struct BwdWs { size_t fmean, gmean, reach, reach_stride, flag, hx, blkmax, blkmax_stride, cls, total; int nblk; };
 static BwdWs bwd_layout(int B, int V, int arr_rows, int W) {
   BwdWs w;
   const size_t planes = (size_t)B * V;
@@ -666,6 +647,7 @@ static BwdWs bwd_layout(int B, int V, int arr_rows, int W) {
   w.reach_stride = align_up(planes * sizeof(int), 256);
   w.reach = off; off += 3 * w.reach_stride;
   w.flag = off; off += align_up(planes, 256);
+  w.hx = off; off += 65536 * sizeof(int);          // longitudinal reach per arrival row (rows kernel)
   w.blkmax_stride = align_up(planes * (size_t)w.nblk, 256);
   w.blkmax = off; off += 3 * w.blkmax_stride;
   w.cls = off; off += align_up(planes * (size_t)arr_rows * W, 256);
@@ -795,6 +777,79 @@ static bool plan_sweep(const Params& P, float cfl_cells, int planes, int capacit
   return true;
 }
 
+
+// ---- plan + launch of the warp-specialised row sweep (sl_rows.cuh) -------------------------------
+// hx_tab[y] = longitudinal reach of arrival row y in cells (1 << 20: unbounded, scan the whole circle); also clears
+// the per-plane contract flags.  One tiny launch in front of the sweep.
+__global__ void rows_prep_kernel(const float* __restrict__ sin_lat, const float* __restrict__ cos_lat, int H,
+                                 ReachModel reach, int* __restrict__ hx_tab, unsigned char* __restrict__ flag, int planes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H) hx_tab[i] = halo_cells(reach, sin_lat[i], cos_lat[i]);
+  if (i < planes) flag[i] = 0;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <bool EXACT, int INTERP>
+static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const BwdWs& L, char* ws) {
+  constexpr int NT = Stencil<INTERP>::NT;
+  const int H = P.H, W = P.W, planes = P.B * P.V;
+  if (!(cfl_cells > 0.0f) || H < 8 || W < 32 || W > 32767) return false;
+  const int rr = (int)ceil((double)cfl_cells);
+  const double dphi = (double)P.d_lat / (H - 1), dlam = (double)P.d_lon / (W - 1);
+  const double delta = (double)cfl_cells * dphi;
+  if (rr > 40 || delta > 0.7) return false;
+  RowsPlan S;
+  memset(&S, 0, sizeof(S));
+  S.planes = planes; S.rr = rr; S.ring = 2 * rr + NT;
+  static const int env_nc = env_int("PARADIS_SL_ROWS_NC", 0);
+  int nC = env_nc > 0 ? env_nc : (INTERP == 1 ? 6 : 9);
+  if (nC > kRowsWarps - 2) nC = kRowsWarps - 2;
+  int wc = ((W + nC - 1) / nC + 3) & ~3;
+  if (wc < 32) wc = 32;
+  nC = (W + wc - 1) / wc;
+  S.nC = nC; S.wc = wc; S.nP = kRowsWarps - 1 - nC;
+  S.nsteps = (W + 32 * kStepSub - 1) / (32 * kStepSub);
+  S.total_rows = planes * P.ownN;
+  S.min_seg = 2 * S.ring;
+  size_t off = (size_t)S.ring * W * sizeof(float);
+  S.off_stage = (unsigned)off; off += (size_t)kRowStages * 3 * W * sizeof(float);
+  S.off_rec = (unsigned)off; off += (size_t)kRowRecs * W * sizeof(float4);
+  S.off_tag = (unsigned)off; off += (size_t)nC * kTagBytes;
+  S.off_bar = (unsigned)off; off += (2 * kRowStages + 2 * kRowRecs) * sizeof(uint64_t);
+  const size_t smem = off;
+  if (smem > 227 * 1024) return false;
+  auto kern = (P.f_halo > 0 || P.a_halo > 0) ? sl_bwd_rows_kernel<EXACT, INTERP, true> : sl_bwd_rows_kernel<EXACT, INTERP, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  int dev = 0, nsm = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  ReachModel reach;
+  reach.sin_delta = (float)sin(delta); reach.cos_delta = (float)cos(delta);
+  reach.inv_dlam = (float)(1.0 / dlam); reach.extra = NT + 2; reach.max_halo = 0;
+  int* hx_tab = (int*)(ws + L.hx);
+  unsigned char* flag = (unsigned char*)(ws + L.flag);
+  const int nprep = H > planes ? H : planes;
+  rows_prep_kernel<<<(nprep + 255) / 256, 256, 0, st>>>(P.sin_lat, P.cos_lat, H, reach, hx_tab, flag, planes);
+  S.hx_tab = hx_tab; S.plane_flag = flag; S.out0 = P.own0; S.outN = P.ownN;
+  static const int env_rows = env_int("PARADIS_SL_ROWS_PER_CTA", 24);
+  int grid = S.total_rows / (env_rows > 0 ? env_rows : 24);
+  if (grid < 1) grid = 1;
+  if (grid > nsm) grid = nsm;
+  kern<<<grid, kRowsWarps * 32, smem, st>>>(P, S);
+  if (P.pole_fix) {
+    // adjoint of the first enforce_pole_continuity (advection.py:129): pole rows of grad_field get their zonal mean
+    const int warps = planes * 2;
+    pole_rows_fix_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(P.gfield, P.ownN, P.own0, H, W, planes);
+  }
+  return true;
+}
+
 // Side streams for the two polar caps (they run beside the sweep, which leaves issue slots idle).
 // Created once per host thread and device; fork/join with events, so the call stays asynchronous
 // and capturable.  This is the only resource the library keeps between calls.
@@ -834,6 +889,15 @@ static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_
   if (!want_field || phases != PARADIS_BWD_ALL || !(cfl_cells > 0.0f) || vec != 4)   // the sweep needs float4 rows
     return launch_general<EXACT, INTERP>(P, vec, st, want_field, phases, L.nblk);
 
+  // ---- warp-specialised row sweep (all latitudes); planes that break its contract fall back below
+  static const int bwd_mode = env_int("PARADIS_SL_BWD", 0);      // experiments: 1 = round-1 strip sweep, 2 = general path only
+  if (bwd_mode == 2) return launch_general<EXACT, INTERP>(P, vec, st, want_field, phases, L.nblk);
+  if (bwd_mode == 0 && launch_rows<EXACT, INTERP>(P, st, cfl_cells, L, ws)) {
+    Params Q = P;
+    Q.plane_filter = (unsigned char*)(ws + L.flag);
+    Q.gu = nullptr; Q.gv = nullptr;                   // grad_u / grad_v are already complete
+    return launch_general<EXACT, INTERP>(Q, vec, st, true, PARADIS_BWD_ALL, L.nblk);
+  }
   // ---- fused sweep over the mid-latitudes
   constexpr int NT = Stencil<INTERP>::NT;
   SweepPlan S;

@@ -77,6 +77,7 @@ struct SweepPlan {
   int out0, outN;                             // rows held by the output tensors (global first row, count)
 };
 
+#define PSL_HAVE_RESOLVE_CLASHES 1
 template <int NT>
 __device__ __forceinline__ void resolve_clashes(int key, int tkey, unsigned char* tag, int lane,
                                                 float (&c)[NT * NT], bool& writer) {
@@ -150,7 +151,7 @@ __device__ __forceinline__ void sweep_compute(const Params& P, const SweepRow& R
     if (R.gu_row) {
       float val, ddx, ddy;
       stencil_eval<INTERP, true, PEER>(P, f, pl, t, mean0, mean1, val, ddx, ddy);
-      velocity_grads(P, t, R.sp, R.cp, g * ddx, g * ddy, ou, ov);
+      velocity_grads<EXACT>(P, t, R.sp, R.cp, g * ddx, g * ddy, ou, ov);
     }
 #endif
   }

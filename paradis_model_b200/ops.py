@@ -27,10 +27,30 @@ _status_words: dict = {}
 
 
 def _status_word(device: torch.device) -> Tensor:
+    """One int32 per device in MAPPED PINNED HOST memory (cudaHostAlloc memory is device-accessible
+    under UVA): a kernel that detects a contract violation stores the code straight into host memory,
+    so the host can look at it at the start of every later call without a synchronisation or a copy."""
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     if key not in _status_words:
-        _status_words[key] = torch.zeros(1, dtype=torch.int32, device=device)
+        _status_words[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
     return _status_words[key]
+
+
+def _raise_status(word: Tensor) -> None:
+    code = int(word[0])
+    word.zero_()
+    raise RuntimeError(f"paradis_sl device status {_lib.STATUS_NAMES.get(code, code)}: "
+                       "semi-Lagrangian displacement outside the supported window (more than "
+                       f"{_lib.MAX_DISP_ROWS} rows, or a departure stencil outside a latitude band's halo) "
+                       "in this or an earlier call on this device")
+
+
+def poll_status(device) -> None:
+    """Non-blocking check, run at the start of every operator call: raises if a kernel of an EARLIER call has
+    reported a contract violation by now.  Costs one host memory read."""
+    word = _status_word(torch.device(device))
+    if int(word[0]):
+        _raise_status(word)
 
 
 def check_status(device=None) -> None:
@@ -39,11 +59,9 @@ def check_status(device=None) -> None:
     ``field`` in a latitude-band call)."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     word = _status_word(device)
-    code = int(word.item())
-    if code:
-        word.zero_()
-        raise RuntimeError(f"paradis_sl device status {_lib.STATUS_NAMES.get(code, code)}: "
-                           "semi-Lagrangian displacement outside the supported window")
+    torch.cuda.synchronize(device)
+    if int(word[0]):
+        _raise_status(word)
 
 
 def _stream(t: Tensor) -> C.c_void_p:
@@ -185,6 +203,10 @@ def _sl_advect(field: Tensor, u: Tensor, v: Tensor, tables: Tensor, scalars: Lis
                interp: int, pole_fix: bool, math: int, windows: List[int], cfl: float) -> Tensor:
     B, V, H, W, ownN, arrN = _check_inputs(field, u, v, windows)
     L = _lib.lib()
+    poll_status(field.device)
+    if tables.device != field.device:
+        raise RuntimeError(f"paradis::sl_advect: geometry tables live on {tables.device}, the tensors on {field.device}; "
+                           "move the geometry with SLGeometry.to(device)")
     field = _inner_contig(field.float())
     u = _inner_contig(u.float())
     v = _inner_contig(v.float())
@@ -214,6 +236,9 @@ def _sl_advect_backward(grad_out: Tensor, field: Tensor, u: Tensor, v: Tensor, t
     B, V, H, W, ownN, arrN = _check_inputs(field, u, v, windows)
     L = _lib.lib()
     dev = field.device
+    poll_status(dev)
+    if tables.device != dev:
+        raise RuntimeError(f"paradis::sl_advect_backward: geometry tables live on {tables.device}, the tensors on {dev}")
     field = _inner_contig(field.float())
     u = _inner_contig(u.float())
     v = _inner_contig(v.float())

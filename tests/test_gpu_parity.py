@@ -118,7 +118,55 @@ def test_exact_mode_vs_same_device_torch(interp):
     print("exact-vs-torch-cuda", interp, errs, bad)
     assert errs[0] < 1e-4 and bad[0] == 0.0, errs      # white-noise field: one ulp of ix is ~3e-5 of max|out|
     assert errs[1] < 1e-4, errs
-    assert bad[2] < 1e-4 and bad[3] < 1e-4, bad
+    # identical coordinates => no cell-edge flips: grad_u / grad_v must meet the north_star 1e-4 EVERYWHERE
+    assert errs[2] < 1e-4 and errs[3] < 1e-4 and bad[2] == 0.0 and bad[3] == 0.0, (errs, bad)
+
+
+# ------------------------------------------------------------------ value parity at the headline size (0.25 deg)
+_C3_ORACLE = {}
+
+
+def _c3_smooth(interp):
+    """721x1440 pole-including mesh, smooth field and ~4-cell smooth velocities, CPU oracle (cached per stencil)."""
+    if interp not in _C3_ORACLE:
+        H, W, B, V = 721, 1440, 1, 3
+        lat, lon = O.make_grids(H, W, True)
+        field = O.smooth_field(lat, lon, B, V).float()
+        u, v = [t.float() for t in O.smooth_velocity(lat, lon, B, V, 4.0, DT)]
+        go = O.smooth_field(lat, lon, B, V, seed=7).float()
+        _C3_ORACLE[interp] = (lat, lon, field, u, v, go, O.sl_advect_fwd_bwd(field, u, v, lat, lon, DT, go, interp))
+    return _C3_ORACLE[interp]
+
+
+@pytest.mark.parametrize("cfl", [6.0, 0.0], ids=["rowsweep", "general"])
+@pytest.mark.parametrize("math_mode", ["fast", "exact"])
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+def test_c3_size_values_vs_cpu_oracle(interp, math_mode, cfl):
+    """out, grad_field, grad_u, grad_v at 721x1440 (polar rows with 1/cos(lat) reach, cap folds, pole means, both
+    backward paths) against the CPU oracle: north_star tolerances, forward 1e-5, gradients 1e-4 (relative to max)."""
+    lat, lon, field, u, v, go, ref = _c3_smooth(interp)
+    got = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, math_mode, cfl=cfl)
+    errs = [relmax(a, b) for a, b in zip(got, ref)]
+    print("c3 smooth", interp, math_mode, cfl, errs)
+    assert errs[0] < 1e-5, errs
+    assert errs[1] < 1e-4, errs
+    # smooth fields: d out / d ix is continuous enough that a cell-edge flip moves grad_u / grad_v by << 1e-4
+    assert errs[2] < 1e-4 and errs[3] < 1e-4, errs
+
+
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+def test_c3_size_exact_mode_white_noise_vs_same_device_torch(interp):
+    """White noise at 721x1440, V=8, EXACT mode, row-sweep backward, against the oracle's op replay run by torch on
+    the same GPU (bit-identical coordinates): every output within tolerance, no outliers."""
+    H, W, B, V = 721, 1440, 1, 8
+    lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, True, DT)
+    dev = [t.cuda() for t in (field, u, v, lat, lon, go)]
+    ref = [t.cpu() for t in O.sl_advect_fwd_bwd(dev[0], dev[1], dev[2], dev[3], dev[4], DT, dev[5], interp)]
+    got = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, "exact", cfl=6.0)
+    errs = [relmax(a, b) for a, b in zip(got, ref)]
+    print("c3 exact-vs-torch-cuda", interp, errs)
+    assert errs[0] < 1e-5, errs                      # identical stencil indices and weights: rounding of the sums only
+    assert errs[1] < 1e-4 and errs[2] < 1e-4 and errs[3] < 1e-4, errs
 
 
 def test_fast_mode_white_noise_statistics():
