@@ -141,6 +141,54 @@ __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
   }
 }
 
+// FAST-math forward, round 2: the own rows of a plane are one flat array of points; a warp takes 128
+// consecutive points, lane l the points l, l + 32, l + 64, l + 96 -- consecutive lanes on consecutive columns, so
+// every load, store and stencil tap of a warp touches one or two 128-byte lines (the float4-per-thread layout
+// spread the 4 taps of a warp over 5 lines each: the L1 data pipe was 77 % busy) -- and the 4 departure points
+// are computed as two packed pairs (FFMA2 / FMUL2 / FADD2: two points per instruction).  Any W, any alignment.
+template <int INTERP, bool PEER>
+__global__ void __launch_bounds__(256) sl_fwd_pair_kernel(const Params P, const int gpr) {
+  // one warp = 128 consecutive columns of one row (gpr groups per row; the last group of a row may be short)
+  const int c = blockIdx.y, b = blockIdx.z, pl = b * P.V + c;
+  const int lane = threadIdx.x & 31;
+  const int G = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int r = G / gpr;
+  if (r >= P.ownN) return;
+  const int xb = (G - r * gpr) * 128 + lane, y = P.own0 + r;
+  const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
+  const float* f = plane_ptr_bc(P.field, P.field_sB, b, c, P.fldN, P.W);
+  const int aoff = (y - P.uvg0) * P.W;
+  const float* up = plane_ptr_bc(P.u, P.u_sB, b, c, P.uvgN, P.W) + aoff;
+  const float* vp = plane_ptr_bc(P.v, P.v_sB, b, c, P.uvgN, P.W) + aoff;
+  float* op = P.out + ((long long)pl * P.ownN + r) * P.W;
+  float mean0 = 0.0f, mean1 = 0.0f;
+  if (P.pole_fix) { mean0 = __ldg(P.fmean + 2 * pl); mean1 = __ldg(P.fmean + 2 * pl + 1); }
+  float uu[4], vv[4], ll[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = min(xb + 32 * k, P.W - 1);              // lanes past the row end redo its last point (not stored)
+    uu[k] = __ldcs(up + x); vv[k] = __ldcs(vp + x); ll[k] = __ldg(P.lon + x);
+  }
+  float oo[4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (xb - lane + 64 * h < P.W) {                        // uniform: skip a pair that lies past the row end
+      Traj2 t2;
+      trajectory_2(P, make_float2(uu[2 * h], uu[2 * h + 1]), make_float2(vv[2 * h], vv[2 * h + 1]), f2s(sp), f2s(cp),
+                   make_float2(ll[2 * h], ll[2 * h + 1]), t2);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const Traj t = traj_half(t2, e);
+        float dx, dy;
+        stencil_eval<INTERP, false, PEER>(P, f, pl, t, mean0, mean1, oo[2 * h + e], dx, dy);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (xb + 32 * k < P.W) __stcs(op + xb + 32 * k, oo[k]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // backward, per arrival point: grad_u, grad_v and the row class of the departure cell
 // ---------------------------------------------------------------------------------------------
@@ -624,7 +672,15 @@ extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* f
   const unsigned units = (unsigned)P.ownN * P.upr;
   dim3 grid((units + 255) / 256, V, B);
   const bool exact = math == PARADIS_MATH_EXACT;
-  if (interp == 1) { if (exact) launch_fwd<true, 1>(P, vec, grid, st); else launch_fwd<false, 1>(P, vec, grid, st); }
+  // experiments: PARADIS_SL_FWD=2 selects the packed-pair forward (consecutive lanes on consecutive columns, FFMA2
+  // trajectory): bit-identical output, measured 0.43 ms against 0.38 ms for the float4-per-thread kernel at C3
+  static const int fwd_mode = getenv("PARADIS_SL_FWD") ? atoi(getenv("PARADIS_SL_FWD")) : 0;
+  if (!exact && interp == 1 && fwd_mode == 2) {
+    const int gpr = (P.W + 127) / 128;
+    dim3 pgrid((unsigned)(((long long)gpr * P.ownN + 7) / 8), V, B);       // 8 warps per CTA
+    if (P.f_halo > 0) sl_fwd_pair_kernel<1, true><<<pgrid, 256, 0, st>>>(P, gpr);
+    else sl_fwd_pair_kernel<1, false><<<pgrid, 256, 0, st>>>(P, gpr);
+  } else if (interp == 1) { if (exact) launch_fwd<true, 1>(P, vec, grid, st); else launch_fwd<false, 1>(P, vec, grid, st); }
   else             { if (exact) launch_fwd<true, 2>(P, vec, grid, st); else launch_fwd<false, 2>(P, vec, grid, st); }
   if (pole_fix) {
     const int warps = planes * 2;
@@ -633,9 +689,9 @@ extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* f
   return check_launch("paradis_sl_advect_fwd");
 }
 
-// workspace layout (backward): fmean | gmean | plane_reach[3] | plane_flag | hx | blkmax[3] | cls
+// workspace layout (backward): fmean | gmean | plane_reach[3] | plane_flag | hx | guard | blkmax[3] | cls
 // (three reach / blkmax sets: the two polar caps run concurrently with the sweep, then the fallback)
-struct BwdWs { size_t fmean, gmean, reach, reach_stride, flag, hx, blkmax, blkmax_stride, cls, total; int nblk; };
+struct BwdWs { size_t fmean, gmean, reach, reach_stride, flag, hx, guard, blkmax, blkmax_stride, cls, total; int nblk; };
 static BwdWs bwd_layout(int B, int V, int arr_rows, int W) {
   BwdWs w;
   const size_t planes = (size_t)B * V;
@@ -648,6 +704,8 @@ static BwdWs bwd_layout(int B, int V, int arr_rows, int W) {
   w.reach = off; off += 3 * w.reach_stride;
   w.flag = off; off += align_up(planes, 256);
   w.hx = off; off += 65536 * sizeof(int);          // longitudinal reach per arrival row (rows kernel)
+  // guard columns of the rows kernel: [planes][rows][consumers][NT - 1]
+  w.guard = off; off += align_up(planes * (size_t)arr_rows * kRowsWarps * kStreams * 3 * sizeof(float), 256);
   w.blkmax_stride = align_up(planes * (size_t)w.nblk, 256);
   w.blkmax = off; off += 3 * w.blkmax_stride;
   w.cls = off; off += align_up(planes * (size_t)arr_rows * W, 256);
@@ -806,19 +864,23 @@ static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const
   memset(&S, 0, sizeof(S));
   S.planes = planes; S.rr = rr; S.ring = 2 * rr + NT;
   static const int env_nc = env_int("PARADIS_SL_ROWS_NC", 0);
-  int nC = env_nc > 0 ? env_nc : (INTERP == 1 ? 6 : 9);
+  int nC = env_nc > 0 ? env_nc : (INTERP == 1 ? 5 : 8);
   if (nC > kRowsWarps - 2) nC = kRowsWarps - 2;
-  int wc = ((W + nC - 1) / nC + 3) & ~3;
+  int nS = nC * kStreams;                                  // strips: kStreams per consumer warp
+  int wc = ((W + nS - 1) / nS + 3) & ~3;
   if (wc < 32) wc = 32;
-  nC = (W + wc - 1) / wc;
-  S.nC = nC; S.wc = wc; S.nP = kRowsWarps - 1 - nC;
+  nS = (W + wc - 1) / wc;
+  nC = (nS + kStreams - 1) / kStreams;
+  S.nC = nC; S.nS = nS; S.wc = wc; S.nP = kRowsWarps - 1 - nC;
+  if (S.nP < 1) return false;
   S.nsteps = (W + 32 * kStepSub - 1) / (32 * kStepSub);
   S.total_rows = planes * P.ownN;
-  S.min_seg = 2 * S.ring;
-  size_t off = (size_t)S.ring * W * sizeof(float);
+  S.pitch = (wc + NT - 1 + 3) & ~3;
+  S.ring_stride = (S.ring + NT - 1) * S.pitch;
+  size_t off = (size_t)nS * S.ring_stride * sizeof(float);
   S.off_stage = (unsigned)off; off += (size_t)kRowStages * 3 * W * sizeof(float);
   S.off_rec = (unsigned)off; off += (size_t)kRowRecs * W * sizeof(float4);
-  S.off_tag = (unsigned)off; off += (size_t)nC * kTagBytes;
+  S.off_tag = (unsigned)off; off += (size_t)nS * kTagBytes;
   S.off_bar = (unsigned)off; off += (2 * kRowStages + 2 * kRowRecs) * sizeof(uint64_t);
   const size_t smem = off;
   if (smem > 227 * 1024) return false;
@@ -837,11 +899,52 @@ static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const
   const int nprep = H > planes ? H : planes;
   rows_prep_kernel<<<(nprep + 255) / 256, 256, 0, st>>>(P.sin_lat, P.cos_lat, H, reach, hx_tab, flag, planes);
   S.hx_tab = hx_tab; S.plane_flag = flag; S.out0 = P.own0; S.outN = P.ownN;
+  S.guard = (float*)(ws + L.guard);
   static const int env_rows = env_int("PARADIS_SL_ROWS_PER_CTA", 24);
   int grid = S.total_rows / (env_rows > 0 ? env_rows : 24);
   if (grid < 1) grid = 1;
   if (grid > nsm) grid = nsm;
+  if (grid > kRowsMaxCtas) grid = kRowsMaxCtas;
+  {
+    // Cost-balanced partition.  A row costs the consumers k(y) = steps of 32 records they scan for it (the whole
+    // circle near the poles) plus a constant for the producers' share; CTA boundaries are placed at equal cumulative
+    // cost and snapped onto a plane boundary when they fall within min_seg rows of one (a segment costs ring - 1
+    // extra arrival rows).  Only balance depends on this model, results do not.
+    static const int env_w0 = env_int("PARADIS_SL_ROWS_W0", 6);
+    const int ownN = P.ownN, min_seg = 2 * S.ring;
+    std::vector<double> pre(ownN + 1, 0.0);
+    for (int r = 0; r < ownN; ++r) {
+      const double lat = (double)P.min_lat + (P.own0 + r) * dphi;
+      const int hx = halo_cells(reach, (float)sin(lat), (float)cos(lat));
+      int len = wc + 2 * (hx < W ? hx : W);
+      if (len > W) len = W;
+      int k = (len + 31) >> 5;
+      if ((k & 3) == 0) ++k;
+      pre[r + 1] = pre[r] + env_w0 + k;
+    }
+    const double per_plane = pre[ownN], total = per_plane * planes;
+    S.bound[0] = 0;
+    for (int c = 1; c < grid; ++c) {
+      const double goal = total * c / grid;
+      int pl = (int)(goal / per_plane);
+      if (pl >= planes) pl = planes - 1;
+      const double rem = goal - pl * per_plane;
+      int r = (int)(std::upper_bound(pre.begin(), pre.end(), rem) - pre.begin()) - 1;
+      if (r < 0) r = 0;
+      if (r > ownN) r = ownN;
+      if (r < min_seg) r = 0;
+      else if (ownN - r < min_seg) { r = 0; ++pl; }
+      int b = pl * ownN + r;
+      if (b < S.bound[c - 1]) b = S.bound[c - 1];
+      S.bound[c] = b;
+    }
+    S.bound[grid] = S.total_rows;
+  }
   kern<<<grid, kRowsWarps * 32, smem, st>>>(P, S);
+  {
+    const long long nfix = (long long)S.total_rows * nS * (NT - 1);
+    rows_guard_fix_kernel<<<(unsigned)((nfix + 255) / 256), 256, 0, st>>>(P.gfield, S.guard, S.total_rows, W, nS, wc, NT - 1);
+  }
   if (P.pole_fix) {
     // adjoint of the first enforce_pole_continuity (advection.py:129): pole rows of grad_field get their zonal mean
     const int warps = planes * 2;
@@ -892,7 +995,9 @@ static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_
   // ---- warp-specialised row sweep (all latitudes); planes that break its contract fall back below
   static const int bwd_mode = env_int("PARADIS_SL_BWD", 0);      // experiments: 1 = round-1 strip sweep, 2 = general path only
   if (bwd_mode == 2) return launch_general<EXACT, INTERP>(P, vec, st, want_field, phases, L.nblk);
-  if (bwd_mode == 0 && launch_rows<EXACT, INTERP>(P, st, cfl_cells, L, ws)) {
+  // (4x4 stencil: the round-1 strip sweep is still the faster kernel, 3.65 against 4.6 ms at C3; PARADIS_SL_BWD=3
+  // forces the row sweep for it)
+  if ((bwd_mode == 3 || (bwd_mode == 0 && INTERP == 1)) && launch_rows<EXACT, INTERP>(P, st, cfl_cells, L, ws)) {
     Params Q = P;
     Q.plane_filter = (unsigned char*)(ws + L.flag);
     Q.gu = nullptr; Q.gv = nullptr;                   // grad_u / grad_v are already complete

@@ -39,22 +39,41 @@
 
 namespace psl {
 
-constexpr int kRowStages = 2;      // u, v, grad_out rows in flight (TMA)
-constexpr int kRowRecs = 3;        // record rows in flight between producers and consumers
-constexpr int kStepSub = 4;        // 32-column sub-blocks per producer step
-constexpr int kTagBytes = 1024;    // clash tags per consumer warp (hashed, power of two)
+#ifndef PSL_ROWS_STAGES
+#define PSL_ROWS_STAGES 2
+#endif
+#ifndef PSL_ROWS_RECS
+#define PSL_ROWS_RECS 3
+#endif
+constexpr int kRowStages = PSL_ROWS_STAGES;   // u, v, grad_out rows in flight (TMA)
+constexpr int kRowRecs = PSL_ROWS_RECS;       // record rows in flight between producers and consumers
+#ifndef PSL_ROWS_SUB
+#define PSL_ROWS_SUB 4
+#endif
+constexpr int kStepSub = PSL_ROWS_SUB;   // 32-column sub-blocks per producer step
+constexpr int kTagBytes = 512;     // clash tags per strip (hashed, power of two)
+#ifndef PSL_ROWS_STREAMS
+#define PSL_ROWS_STREAMS 1
+#endif
+constexpr int kStreams = PSL_ROWS_STREAMS;   // strips a consumer warp works on in an interleaved manner
+constexpr int kRowsMaxCtas = 192;
 #ifndef PSL_ROWS_WARPS
-#define PSL_ROWS_WARPS 24          // loader + producers + consumers; 24 warps = 768 threads -> 80 registers
+#define PSL_ROWS_WARPS 20          // loader + producers + consumers; 20 warps = 640 threads -> 96 registers, no spills
 #endif
 constexpr int kRowsWarps = PSL_ROWS_WARPS;
 
 struct RowsPlan {
   int planes, rr, ring;            // ring = 2 rr + NT destination rows
   int nP, nC;                      // producer / consumer warps (warp 0 is the loader)
-  int wc;                          // consumer strip width (multiple of 4)
+  int nS;                          // strips = private rings (kStreams per consumer warp)
+  int wc;                          // strip width (multiple of 4)
+  int pitch, ring_stride;          // private ring of a consumer: (ring + NT - 1) rows of `pitch` floats = ring_stride
+  float* guard;                    // [planes][outN][nS][NT - 1] guard columns of the retired rows (added by a post-kernel)
   int nsteps;                      // producer steps per arrival row = ceil(W / 128)
   int total_rows;                  // planes * ownN
-  int min_seg;                     // CTA boundaries closer than this to a plane boundary snap onto it
+  int bound[kRowsMaxCtas + 1];     // CTA k owns rows [bound[k], bound[k + 1]) of the concatenated (plane, own row)
+                                   // space: equal COST (rows near the poles keep the consumers busy several times
+                                   // longer), boundaries close to a plane boundary snapped onto it (host plan)
   const int* __restrict__ hx_tab;  // [H] longitudinal reach (cells) of an arrival row; >= W: whole circle
   unsigned char* plane_flag;       // [planes] set to 1 on a contract violation
   int out0, outN;                  // rows held by the output tensors
@@ -73,6 +92,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t byte
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  // (a suspend-time hint on try_wait was measured: fewer polls, but 3 % slower overall)
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -89,17 +109,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-
-// ---- work partition: CTA k of n owns the rows [rows_bound(k), rows_bound(k + 1)) of the concatenated
-// (plane, own row) space; boundaries close to a plane boundary snap onto it (a segment costs ring - 1
-// extra arrival rows of trajectory work).
-__device__ __forceinline__ int rows_bound(const RowsPlan& S, int ownN, int k, int n) {
-  const long long t = (long long)k * S.total_rows / n;
-  int pl = (int)(t / ownN), r = (int)(t - (long long)pl * ownN);
-  if (r < S.min_seg) r = 0;
-  else if (ownN - r < S.min_seg) { r = 0; ++pl; }
-  return pl * ownN + r;
 }
 
 struct RowsSeg { int pl, ra, rb, y_first, y_last; };   // destination rows [ra, rb) of plane pl (global rows)
@@ -119,16 +128,12 @@ __device__ __forceinline__ bool rows_next_seg(const Params& P, const RowsPlan& S
   return true;
 }
 
-#ifndef PSL_HAVE_RESOLVE_CLASHES
-template <int NT>
-__device__ __forceinline__ void resolve_clashes(int key, int tkey, unsigned char* tag, int lane,
-                                                float (&c)[NT * NT], bool& writer) {
-  // tkey: tag slot (hashed; a false alias only costs one pass of the loop below)
-  if (key >= 0) tag[tkey] = (unsigned char)lane;
-  __syncwarp();
-  const bool lost = (key >= 0) && (tag[tkey] != (unsigned char)lane);
+// Lanes of one step that hit the same departure cell: every clashing cell is resolved by a ballot on the exact key
+// and summed into its lowest lane in ascending lane order (single writer, data-defined order).  `lost`: this lane
+// found another lane's id in the tag of its cell (a hashed tag may alias: that only costs a pass of the loop).
+template <int NN>
+__device__ __forceinline__ void rows_resolve_pending(int key, bool lost, int lane, float (&c)[NN], bool& writer) {
   unsigned pending = __ballot_sync(0xffffffffu, lost);
-  writer = key >= 0;
   while (pending) {  // uniform loop: one iteration per clashing cell
     const int j = __ffs(pending) - 1;
     const int kj = __shfl_sync(0xffffffffu, key, j);
@@ -140,7 +145,7 @@ __device__ __forceinline__ void resolve_clashes(int key, int tkey, unsigned char
       const int src = __ffs(rest) - 1;
       rest &= rest - 1;
 #pragma unroll
-      for (int t = 0; t < NT * NT; ++t) {
+      for (int t = 0; t < NN; ++t) {
         const float o = __shfl_sync(0xffffffffu, c[t], src);
         if (lane == leader) c[t] += o;
       }
@@ -148,55 +153,98 @@ __device__ __forceinline__ void resolve_clashes(int key, int tkey, unsigned char
     if (lane != leader && ((group >> lane) & 1u)) writer = false;
   }
 }
-#endif
 
-// Record key: bits [31:16] row class + rr (0 .. 2 rr), bit 15: the last tap column lies outside the padded
-// plane (padding_mode="zeros"), bits [14:0] unpadded column of tap 0 wrapped into [0, W).  < 0: no contribution.
-__device__ __forceinline__ int rows_key(int t, int col0, bool last_out) { return (t << 16) | (last_out ? 0x8000 : 0) | col0; }
+// Record (16 bytes per arrival point, written once by its producer, read by the consumer(s) it concerns):
+//   2x2 stencil: { g * (1 - tx), g * tx, ty, key }      4x4 stencil: { tx, ty, g, key }
+// key: bits [31:16] ring slot of tap row 0 (the producer knows the row sequence of the segment), bit 15: the last
+// tap column lies outside the padded plane (padding_mode="zeros"), bits [14:0] unpadded column of tap 0 wrapped
+// into [0, W).  key < 0: no contribution (contract violated or non-finite coordinates).
+__device__ __forceinline__ int rows_key(int slot0, int col0, bool last_out) {
+  return (slot0 << 16) | (last_out ? 0x8000 : 0) | col0;
+}
 
-// ---- consumer: one 32-record step, rows whose stencils stay inside rows 0 .. H-1 (no cap fold) -----
+// The NT x NT contributions g * wy[a] * wx[b] of a record.
 template <int INTERP>
-__device__ __forceinline__ void rows_scatter_plain(const float4 rec, bool inr, float* ring_base, unsigned char* tag,
-                                                   int W, int ring, int head, int ja, int wc, int lane) {
+__device__ __forceinline__ void rows_weights(const float4 rec, bool act, bool last_out,
+                                             float (&cc)[Stencil<INTERP>::NT * Stencil<INTERP>::NT]) {
   constexpr int NT = Stencil<INTERP>::NT;
-  const int key = inr ? __float_as_int(rec.w) : -1;
-  const int t = key >> 16, cx = key & 0x7fff;
-  int col[NT];
-  bool own[NT], any_own = false;
+  if (INTERP == 1) {
+    const float gx0 = act ? rec.x : 0.0f, gx1 = (act && !last_out) ? rec.y : 0.0f;
+    const float wy1 = rec.z, wy0 = __fsub_rn(1.0f, wy1);
+    cc[0] = __fmul_rn(gx0, wy0); cc[1] = __fmul_rn(gx1, wy0);
+    cc[2] = __fmul_rn(gx0, wy1); cc[3] = __fmul_rn(gx1, wy1);
+  } else {
+    float wx[NT], wy[NT], d0[NT], d1[NT];
+    axis_weights<INTERP, false>(rec.x, wx, d0);
+    axis_weights<INTERP, false>(rec.y, wy, d1);
+    const float g = act ? rec.z : 0.0f;
+    if (last_out) wx[NT - 1] = 0.0f;
 #pragma unroll
-  for (int b = 0; b < NT; ++b) {
-    int c = cx + b;
-    if (c >= W) c -= W;
-    col[b] = c;
-    own[b] = (unsigned)(c - ja) < (unsigned)wc;
-    any_own = any_own || own[b];
+    for (int a = 0; a < NT; ++a) {
+      const float gw = __fmul_rn(g, wy[a]);
+#pragma unroll
+      for (int b = 0; b < NT; ++b) cc[a * NT + b] = __fmul_rn(gw, wx[b]);
+    }
   }
-  if ((key & 0x8000) != 0) own[NT - 1] = false;
-  const bool act = key >= 0 && any_own;
-  if (!__any_sync(0xffffffffu, act)) return;
-  int s0 = head + t;
-  if (s0 >= ring) s0 -= ring;
-  float wx[NT], wy[NT], d0[NT], d1[NT], cc[NT * NT];
-  axis_weights<INTERP, false>(rec.x, wx, d0);
-  axis_weights<INTERP, false>(rec.y, wy, d1);
-  const float g = act ? rec.z : 0.0f;
+}
+
+// ---- consumer: one step (32 records of each of the warp's kStreams strips), rows whose stencils stay inside
+// rows 0 .. H-1 (no cap fold).
+// A strip's ring is private: `pitch` columns = its wc own columns + NT-1 guard columns (taps that spill into the
+// next strip; a post-kernel adds them to that strip's first columns), ring + NT-1 rows (the last NT-1 alias the
+// first ones, folded together when a row retires).  A record belongs to the strip that owns the column of its
+// tap 0, and all its taps sit at base + a * pitch + b: no wrap, no per-tap ownership test.
+// The strips of a warp are advanced together: their rings are disjoint, so between two warp barriers there are
+// kStreams independent load-add-store chains instead of one (the consumers are latency bound).
+struct RowsStrip { float* ring; unsigned char* tag; int ja, wc; };
+
+template <int INTERP>
+__device__ __forceinline__ void rows_scatter_plain(const float4 (&rec)[kStreams], const bool (&inr)[kStreams],
+                                                   const RowsStrip (&T)[kStreams], int pitch, int lane) {
+  constexpr int NT = Stencil<INTERP>::NT;
+  int key[kStreams], base[kStreams];
+  bool act[kStreams], any_act = false;
+#pragma unroll
+  for (int s = 0; s < kStreams; ++s) {
+    key[s] = inr[s] ? __float_as_int(rec[s].w) : -1;
+    const int rel = (key[s] & 0x7fff) - T[s].ja;
+    act[s] = key[s] >= 0 && (unsigned)rel < (unsigned)T[s].wc;
+    base[s] = (key[s] >> 16) * pitch + rel;
+    any_act = any_act || act[s];
+  }
+  if (!__any_sync(0xffffffffu, any_act)) return;
+  float cc[kStreams][NT * NT];
+  bool lost = false;
+#pragma unroll
+  for (int s = 0; s < kStreams; ++s) {
+    rows_weights<INTERP>(rec[s], act[s], (key[s] & 0x8000) != 0, cc[s]);
+    if (act[s]) T[s].tag[base[s] & (kTagBytes - 1)] = (unsigned char)lane;
+  }
+  __syncwarp();
+  bool writer[kStreams], lst[kStreams];
+#pragma unroll
+  for (int s = 0; s < kStreams; ++s) {
+    lst[s] = act[s] && T[s].tag[base[s] & (kTagBytes - 1)] != (unsigned char)lane;
+    lost = lost || lst[s];
+    writer[s] = act[s];
+  }
+  if (__any_sync(0xffffffffu, lost)) {
+#pragma unroll
+    for (int s = 0; s < kStreams; ++s) rows_resolve_pending<NT * NT>(act[s] ? base[s] : -1, lst[s], lane, cc[s], writer[s]);
+  }
+  float* q[kStreams];
+#pragma unroll
+  for (int s = 0; s < kStreams; ++s) q[s] = T[s].ring + (writer[s] ? base[s] : 0);
 #pragma unroll
   for (int a = 0; a < NT; ++a) {
-    const float gw = __fmul_rn(g, wy[a]);
-#pragma unroll
-    for (int b = 0; b < NT; ++b) cc[a * NT + b] = __fmul_rn(gw, wx[b]);
-  }
-  bool writer;
-  const int k = act ? s0 * W + cx : -1;
-  resolve_clashes<NT>(k, ((s0 & 3) * 257 + cx) & (kTagBytes - 1), tag, lane, cc, writer);
-#pragma unroll
-  for (int a = 0; a < NT; ++a) {
-    int sl = s0 + a;
-    if (sl >= ring) sl -= ring;
-    float* row = ring_base + sl * W;
 #pragma unroll
     for (int b = 0; b < NT; ++b) {
-      if (writer && own[b]) row[col[b]] += cc[a * NT + b];
+      float v[kStreams];
+#pragma unroll
+      for (int s = 0; s < kStreams; ++s) v[s] = writer[s] ? q[s][a * pitch + b] : 0.0f;
+#pragma unroll
+      for (int s = 0; s < kStreams; ++s)
+        if (writer[s]) q[s][a * pitch + b] = v[s] + cc[s][a * NT + b];
       __syncwarp();
     }
   }
@@ -204,34 +252,33 @@ __device__ __forceinline__ void rows_scatter_plain(const float4 rec, bool inr, f
 
 // ---- consumer: one 32-record step of a row near a pole: tap rows outside 0 .. H-1 fold back through the
 // GeoCyclic map (model/padding.py:26-37: reflect about the first / last row excluding it, 180 degrees
-// shifted).  Two points with different departure cells can then meet in one tap phase, but only when one
-// of the taps is folded and the other is not, so every tap phase is split in two (plain taps, then folded
-// taps); within each half distinct departure cells still mean distinct ring cells.
+// shifted), so the owner of a tap row is decided per row (the folded rows belong to the strip half a circle
+// away).  Two points with different departure cells can meet in one tap phase only when one of the taps is
+// folded and the other is not, so every tap phase is split in two (plain taps, then folded taps); within each
+// half distinct departure cells still mean distinct ring cells.
 template <int INTERP>
-__device__ __noinline__ void rows_scatter_fold(int W, int H, const float4 rec, bool inr, float* ring_base,
-                                               unsigned char* tag, int ring, int head, int y, int rr, int ja, int wc,
-                                               int lane) {
+__device__ __noinline__ void rows_scatter_fold(int W, int H, const float4 rec, bool inr, float* myring,
+                                               unsigned char* tag, int pitch, int ring, int head, int y, int rr, int ja,
+                                               int wc, int lane) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
   constexpr int pad = INTERP;                    // padding width = interpolation id (advection.py:22-24)
   const int halfW = W >> 1;
   const int key = inr ? __float_as_int(rec.w) : -1;
-  const int t = key >> 16, cx = key & 0x7fff;
-  const bool last_out = (key & 0x8000) != 0;
+  const int s0 = key >> 16, cx = key & 0x7fff;
+  int t = s0 - head;                              // row class + rr
+  if (t < 0) t += ring;
   const int i0 = y + (t - rr) + OMIN;             // unpadded row of tap row 0
   const int i_ret = y - rr + OMIN;                // row in slot `head`
-  float wx[NT], wy[NT], d0[NT], d1[NT], cc[NT * NT];
-  axis_weights<INTERP, false>(rec.x, wx, d0);
-  axis_weights<INTERP, false>(rec.y, wy, d1);
-  const float g = key >= 0 ? rec.z : 0.0f;
-#pragma unroll
-  for (int a = 0; a < NT; ++a) {
-    const float gw = __fmul_rn(g, wy[a]);
-#pragma unroll
-    for (int b = 0; b < NT; ++b) cc[a * NT + b] = __fmul_rn(gw, wx[b]);
-  }
-  bool writer;
+  float cc[NT * NT];
+  rows_weights<INTERP>(rec, key >= 0, (key & 0x8000) != 0, cc);
   const int k = key >= 0 ? (t * W + cx) : -1;     // same arrival row: (class, column) identifies the departure cell
-  resolve_clashes<NT>(k, ((t & 3) * 257 + cx) & (kTagBytes - 1), tag, lane, cc, writer);
+  if (key >= 0) tag[k & (kTagBytes - 1)] = (unsigned char)lane;
+  __syncwarp();
+  const bool lost = key >= 0 && tag[k & (kTagBytes - 1)] != (unsigned char)lane;
+  bool writer = key >= 0;
+  rows_resolve_pending<NT * NT>(k, lost, lane, cc, writer);
+  int cf = cx - halfW;                            // column of a folded tap row
+  if (cf < 0) cf += W;
 #pragma unroll
   for (int a = 0; a < NT; ++a) {
     int i = i0 + a;
@@ -242,18 +289,16 @@ __device__ __noinline__ void rows_scatter_fold(int W, int H, const float4 rec, b
     int sl = head + (i - i_ret);
     ok = ok && (unsigned)(i - i_ret) < (unsigned)ring;
     if (sl >= ring) sl -= ring;
-    float* row = ring_base + sl * W;
-    const bool any_fold = __any_sync(0xffffffffu, ok && fold);
+    const int rel = (fold ? cf : cx) - ja;
+    const bool mine = ok && (unsigned)rel < (unsigned)wc;
+    float* q = myring + (mine ? sl * pitch + rel : 0);
+    const bool any_fold = __any_sync(0xffffffffu, mine && fold);
 #pragma unroll
     for (int b = 0; b < NT; ++b) {
-      int c = cx + b;
-      if (c >= W) c -= W;
-      if (fold) { c -= halfW; if (c < 0) c += W; }
-      const bool mine = ok && (unsigned)(c - ja) < (unsigned)wc && !(last_out && b == NT - 1);
-      if (mine && !fold) row[c] += cc[a * NT + b];
+      if (mine && !fold) q[b] += cc[a * NT + b];
       __syncwarp();
       if (any_fold) {
-        if (mine && fold) row[c] += cc[a * NT + b];
+        if (mine && fold) q[b] += cc[a * NT + b];
         __syncwarp();
       }
     }
@@ -263,9 +308,9 @@ __device__ __noinline__ void rows_scatter_fold(int W, int H, const float4 rec, b
 // ---- producer: one arrival point -> record (+ grad_u, grad_v for the rows this segment owns) -----
 template <bool EXACT, int INTERP, bool PEER, bool SMALL>
 __device__ __forceinline__ float4 rows_point(const Params& P, const float* __restrict__ f, int pl, float mean0,
-                                             float mean1, float sp, float cp, int y, int x, int rr, int hx, bool core,
-                                             float uu, float vv, float g, float lonp, bool& violated, float& ou,
-                                             float& ov) {
+                                             float mean1, float sp, float cp, int y, int x, int rr, int hx, int hbase,
+                                             int ring, bool core, float uu, float vv, float g, float lonp,
+                                             bool& violated, float& ou, float& ov) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
   Traj t;
   trajectory<EXACT, SMALL>(P, uu, vv, sp, cp, lonp, t);
@@ -285,8 +330,50 @@ __device__ __forceinline__ float4 rows_point(const Params& P, const float* __res
   int col0 = x + dx;
   if (col0 < 0) col0 += P.W; else if (col0 >= P.W) col0 -= P.W;
   const bool valid = in_ring && (unsigned)col0 < (unsigned)P.W;   // false for non-finite coordinates
-  const int key = valid ? rows_key(cls + rr, col0, x0 + NT - 1 >= P.Wp) : -1;
+  int s0 = hbase + cls + rr;                     // ring slot of tap row 0 (hbase: slot of the row retiring after y)
+  if (s0 >= ring) s0 -= ring;
+  const int key = valid ? rows_key(s0, col0, x0 + NT - 1 >= P.Wp) : -1;
+  if (INTERP == 1) return make_float4(__fmul_rn(g, __fsub_rn(1.0f, tx)), __fmul_rn(g, tx), ty, __int_as_float(key));
   return make_float4(tx, ty, g, __int_as_float(key));
+}
+
+// FAST math: two arrival points of one row at a time, trajectory and Jacobian on the packed fp32x2 pipe
+// (bit-identical to rows_point<false, ...> for each of them)
+template <int INTERP, bool PEER>
+__device__ __forceinline__ void rows_pair(const Params& P, const float* __restrict__ f, int pl, float mean0, float mean1,
+                                          float sp, float cp, int y, const int (&x)[2], int rr, int hx, int hbase, int ring,
+                                          bool core, f2 uu, f2 vv, f2 g, f2 lonp, bool& violated, float4 (&rec)[2], f2& ou,
+                                          f2& ov) {
+  constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
+  Traj2 t2;
+  trajectory_2(P, uu, vv, f2s(sp), f2s(cp), lonp, t2);
+  float ddx[2] = {0.0f, 0.0f}, ddy[2] = {0.0f, 0.0f};
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const Traj t = traj_half(t2, e);
+    const float ge = e ? g.y : g.x;
+    const float fx = floorf(t.ix), fy = floorf(t.iy);
+    const float tx = __fsub_rn(t.ix, fx), ty = __fsub_rn(t.iy, fy);
+    const int x0 = (int)fx + OMIN;                 // padded column of tap 0
+    const int cls = (int)fy - (y + P.p);           // row class
+    int dx = x0 - P.p - x[e];                      // longitudinal cell displacement of tap 0
+    if (dx < -P.halfW) dx += P.W; else if (dx >= P.halfW) dx -= P.W;
+    const bool in_ring = (unsigned)(cls + rr) <= (unsigned)(2 * rr);
+    if (!in_ring || dx < -hx || dx > hx - NT + 1) violated = true;
+    if (core) {
+      float val;
+      stencil_eval<INTERP, true, PEER>(P, f, pl, t, mean0, mean1, val, ddx[e], ddy[e]);
+    }
+    int col0 = x[e] + dx;
+    if (col0 < 0) col0 += P.W; else if (col0 >= P.W) col0 -= P.W;
+    const bool valid = in_ring && (unsigned)col0 < (unsigned)P.W;   // false for non-finite coordinates
+    int s0 = hbase + cls + rr;                     // ring slot of tap row 0
+    if (s0 >= ring) s0 -= ring;
+    const int key = valid ? rows_key(s0, col0, x0 + NT - 1 >= P.Wp) : -1;
+    if (INTERP == 1) rec[e] = make_float4(__fmul_rn(ge, __fsub_rn(1.0f, tx)), __fmul_rn(ge, tx), ty, __int_as_float(key));
+    else rec[e] = make_float4(tx, ty, ge, __int_as_float(key));
+  }
+  if (core) velocity_grads_2(P, t2, f2s(sp), f2s(cp), mul2(g, make_float2(ddx[0], ddx[1])), mul2(g, make_float2(ddy[0], ddy[1])), ou, ov);
 }
 
 template <bool EXACT, int INTERP, bool PEER>
@@ -311,8 +398,8 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
   }
   __syncthreads();
 
-  int g = rows_bound(S, P.ownN, blockIdx.x, gridDim.x);
-  const int g1 = rows_bound(S, P.ownN, blockIdx.x + 1, gridDim.x);
+  int g = S.bound[blockIdx.x];
+  const int g1 = S.bound[blockIdx.x + 1];
   const int arr_lo = P.arr0, arr_hi = P.arr0 + P.arrN;
   RowsSeg sg;
 
@@ -373,6 +460,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
         const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
         const int hx = __ldg(S.hx_tab + y);
         const bool core = (y >= sg.ra) && (y < sg.rb) && gu_pl != nullptr;
+        const int hbase = (y - sg.y_first) % ring;     // ring slot of the row that retires after this arrival row
         const bool pole_row = P.pole_fix && (y == 0 || y == P.H - 1);
         const float gpole = y == 0 ? gm0 : gm1;
         for (; next < row_end; next += S.nP) {
@@ -389,22 +477,53 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
           const bool last_step = next + S.nP >= row_end;     // this warp's last step in this row
           __syncwarp();
           if (last_step && lane == 0) mbar_arrive(&stage_free[st]);
-          float4 rec[kStepSub];
-          float ou[kStepSub], ov[kStepSub];
+          // one sub-block after the other, results stored at once: the compiler interleaves as far as the register
+          // budget allows (the kernel runs 1024 threads per SM at 64 registers)
+          float* gu_row = core ? gu_pl + (long long)(y - S.out0) * W : nullptr;
+          float* gv_row = core ? gv_pl + (long long)(y - S.out0) * W : nullptr;
+#if !defined(PSL_DBG_NOPRODUCE) && !defined(PSL_ROWS_NO_PAIRS)
+          if (!EXACT && (kStepSub % 2) == 0) {
 #pragma unroll
-          for (int j = 0; j < kStepSub; ++j)
-            rec[j] = rows_point<EXACT, INTERP, PEER, false>(P, f, pl, mean0, mean1, sp, cp, y, min(xb + 32 * j + lane, W - 1), rr, hx,
-                                                            core, uu[j], vv[j], gg[j], ll[j], violated, ou[j], ov[j]);
-#pragma unroll
-          for (int j = 0; j < kStepSub; ++j) {
-            const int x = xb + 32 * j + lane;
-            if (x < W) {
-              recs[x] = rec[j];
-              if (core) {
-                __stcs(gu_pl + (long long)(y - S.out0) * W + x, ou[j]);
-                __stcs(gv_pl + (long long)(y - S.out0) * W + x, ov[j]);
+            for (int j = 0; j < kStepSub; j += 2) {
+              if (xb + 32 * j < W) {                   // uniform: the last step of a row may be short
+                const int x0 = xb + 32 * j + lane, x1 = x0 + 32;
+                const int xs[2] = {min(x0, W - 1), min(x1, W - 1)};
+                float4 rec[2];
+                f2 ou = f2s(0.0f), ov = f2s(0.0f);
+                rows_pair<INTERP, PEER>(P, f, pl, mean0, mean1, sp, cp, y, xs, rr, hx, hbase, ring, core,
+                                        make_float2(uu[j], uu[j + 1]), make_float2(vv[j], vv[j + 1]),
+                                        make_float2(gg[j], gg[j + 1]), make_float2(ll[j], ll[j + 1]), violated, rec, ou, ov);
+                if (x0 < W) {
+                  recs[x0] = rec[0];
+                  if (core) { __stcs(gu_row + x0, ou.x); __stcs(gv_row + x0, ov.x); }
+                }
+                if (x1 < W) {
+                  recs[x1] = rec[1];
+                  if (core) { __stcs(gu_row + x1, ou.y); __stcs(gv_row + x1, ov.y); }
+                }
               }
             }
+          } else
+#endif
+          {
+#pragma unroll
+          for (int j = 0; j < kStepSub; ++j) {
+            if (xb + 32 * j < W) {                     // uniform: the last step of a row may be short
+              const int x = xb + 32 * j + lane;
+              float ou = 0.0f, ov = 0.0f;
+#ifdef PSL_DBG_NOPRODUCE
+              const float4 rec = make_float4(uu[j], vv[j], gg[j], __int_as_float(rows_key(hbase + rr, min(x, W - 1), false)));
+              ou = uu[j]; ov = vv[j];
+#else
+              const float4 rec = rows_point<EXACT, INTERP, PEER, false>(P, f, pl, mean0, mean1, sp, cp, y, min(x, W - 1), rr, hx,
+                                                                        hbase, ring, core, uu[j], vv[j], gg[j], ll[j], violated, ou, ov);
+#endif
+              if (x < W) {
+                recs[x] = rec;
+                if (core) { __stcs(gu_row + x, ou); __stcs(gv_row + x, ov); }
+              }
+            }
+          }
           }
           if (last_step) {
             __syncwarp();
@@ -424,14 +543,27 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
   if (warp <= S.nP + S.nC) {
     // ==================================== consumers ====================================
     const int cidx = warp - 1 - S.nP;
-    const int ja = cidx * S.wc, jb = min(ja + S.wc, W), wc = jb - ja;
-    unsigned char* tag = smem_raw + S.off_tag + cidx * kTagBytes;
+    const int pitch = S.pitch;
+    RowsStrip T[kStreams];
+    int sidx[kStreams];
+#pragma unroll
+    for (int q = 0; q < kStreams; ++q) {
+      sidx[q] = cidx * kStreams + q;                       // strips past the last one are empty (wc = 0)
+      const int ja = min(sidx[q] * S.wc, W);
+      T[q].ja = ja; T[q].wc = min(ja + S.wc, W) - ja;
+      const int slot = min(sidx[q], S.nS - 1);
+      T[q].ring = ring_base + (size_t)slot * S.ring_stride;
+      T[q].tag = smem_raw + S.off_tag + slot * kTagBytes;
+    }
     int n = 0;
     while (rows_next_seg<INTERP>(P, S, g, g1, sg)) {
       float* gf_pl = P.gfield + (long long)sg.pl * S.outN * W;
-      for (int r = 0; r < ring; ++r)
-        for (int k = 4 * lane; k < wc; k += 128)
-          *reinterpret_cast<float4*>(ring_base + r * W + ja + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+      float* guard_pl = S.guard + (long long)sg.pl * S.outN * S.nS * (NT - 1);
+#pragma unroll
+      for (int q = 0; q < kStreams; ++q)
+        if (T[q].wc > 0)
+          for (int k = 4 * lane; k < S.ring_stride; k += 128)
+            *reinterpret_cast<float4*>(T[q].ring + k) = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
       int head = 0;
       for (int y = sg.y_first; y <= sg.y_last; ++y) {
@@ -440,37 +572,103 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
           mbar_wait(&rec_full[rs], (n / kRowRecs) & 1);
           const float4* recs = rec_base + (size_t)rs * W;
           const int hx = __ldg(S.hx_tab + y);
-          int start = ja - hx, len = wc + 2 * hx;
-          if (hx >= W || len >= W) { start = 0; len = W; }
-          if (start < 0) start += W;
           const bool fold_row = (y + OMIN - rr < 0) || (y + OMIN + rr + NT - 1 >= P.H);
-          for (int s = 0; s < len; s += 32) {
-            const bool inr = s + lane < len;
-            int idx = start + s + lane;
-            if (idx >= W) idx -= W;
-            const float4 rec = inr ? recs[idx] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-            if (fold_row) rows_scatter_fold<INTERP>(W, P.H, rec, inr, ring_base, tag, ring, head, y, rr, ja, wc, lane);
-            else rows_scatter_plain<INTERP>(rec, inr, ring_base, tag, W, ring, head, ja, wc, lane);
+          // Lane l of stream q visits the records start_q + l * k + s, s = 0 .. k-1: the lanes of one step are
+          // k >= len / 32 columns apart, so two of them rarely share a departure cell (consecutive columns clash
+          // about twice per step with white-noise velocities; the records sit in shared memory, any order costs
+          // the same).  k not a multiple of 4: the ring accesses of a step then spread over the banks.
+          int len = S.wc + 2 * hx;
+          const bool whole = hx >= W || len >= W;
+          if (whole) len = W;
+          int k = (len + 31) >> 5;
+          if ((k & 3) == 0) ++k;
+          int idx[kStreams];
+          bool inr[kStreams];
+          float4 rec[kStreams];
+#pragma unroll
+          for (int q = 0; q < kStreams; ++q) {
+            int start = whole ? 0 : T[q].ja - hx;
+            if (start < 0) start += W;
+            idx[q] = start + lane * k;                   // < 2 W + 32
+            if (idx[q] >= W) idx[q] -= W;
+            if (idx[q] >= W) idx[q] -= W;
+            inr[q] = lane * k < len && T[q].wc > 0;
+            rec[q] = inr[q] ? recs[idx[q]] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+          }
+          for (int s = 0; s < k; ++s) {
+            // fetch the next records before the ring updates of these (the compiler cannot move a shared-memory
+            // load across them)
+            float4 nxt[kStreams];
+            bool inn[kStreams];
+#pragma unroll
+            for (int q = 0; q < kStreams; ++q) {
+              idx[q] = idx[q] + 1 == W ? 0 : idx[q] + 1;
+              inn[q] = (s + 1 < k) && (lane * k + s + 1 < len) && T[q].wc > 0;
+              nxt[q] = inn[q] ? recs[idx[q]] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            }
+#ifndef PSL_DBG_NOCONSUME
+            if (fold_row) {
+#pragma unroll
+              for (int q = 0; q < kStreams; ++q)
+                rows_scatter_fold<INTERP>(W, P.H, rec[q], inr[q], T[q].ring, T[q].tag, pitch, ring, head, y, rr, T[q].ja,
+                                          T[q].wc, lane);
+            } else {
+              rows_scatter_plain<INTERP>(rec, inr, T, pitch, lane);
+            }
+#endif
+#pragma unroll
+            for (int q = 0; q < kStreams; ++q) { rec[q] = nxt[q]; inr[q] = inn[q]; }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&rec_free[rs]);
           ++n;
         }
-        // retire destination row i = y - rr + OMIN (slot `head`)
+        // retire destination row i = y - rr + OMIN (slot `head`); slots 0 .. NT-2 first take in their alias rows
         const int i = y - rr + OMIN;
-        float* row = ring_base + head * W + ja;
-        if (i >= sg.ra && i < sg.rb) {
-          float* orow = gf_pl + (long long)(i - S.out0) * W + ja;
-          for (int k = 4 * lane; k < wc; k += 128)
-            __stcs(reinterpret_cast<float4*>(orow + k), *reinterpret_cast<const float4*>(row + k));
+#pragma unroll
+        for (int q = 0; q < kStreams; ++q) {
+          if (T[q].wc <= 0) continue;
+          float* row = T[q].ring + head * pitch;
+          if (head < NT - 1) {
+            float* alias = T[q].ring + (ring + head) * pitch;
+            for (int k = 4 * lane; k < pitch; k += 128) {
+              float4 a = *reinterpret_cast<const float4*>(row + k);
+              const float4 b = *reinterpret_cast<const float4*>(alias + k);
+              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+              *reinterpret_cast<float4*>(row + k) = a;
+              *reinterpret_cast<float4*>(alias + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+          }
+          if (i >= sg.ra && i < sg.rb) {
+            float* orow = gf_pl + (long long)(i - S.out0) * W + T[q].ja;
+            for (int k = 4 * lane; k < T[q].wc; k += 128)
+              __stcs(reinterpret_cast<float4*>(orow + k), *reinterpret_cast<const float4*>(row + k));
+            if (lane < NT - 1)
+              guard_pl[((long long)(i - S.out0) * S.nS + sidx[q]) * (NT - 1) + lane] = row[T[q].wc + lane];
+          }
+          __syncwarp();
+          for (int k = 4 * lane; k < pitch; k += 128) *reinterpret_cast<float4*>(row + k) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncwarp();
-        for (int k = 4 * lane; k < wc; k += 128) *reinterpret_cast<float4*>(row + k) = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
         head = head + 1 == ring ? 0 : head + 1;
       }
     }
   }
+}
+
+// Guard columns (taps that spilled over the end of a consumer's strip) are added to the first columns of the
+// next strip: one thread per (plane, row, strip, guard column); every target cell has one source.
+__global__ void rows_guard_fix_kernel(float* __restrict__ gfield, const float* __restrict__ guard, long long rows_total,
+                                      int W, int nC, int wc, int ng) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_total * nC * ng) return;
+  const int gcol = (int)(idx % ng);
+  const int c = (int)((idx / ng) % nC);
+  const long long row = idx / ((long long)ng * nC);
+  int col = min((c + 1) * wc, W) + gcol;
+  if (col >= W) col -= W;
+  gfield[row * W + col] += guard[idx];
 }
 
 }  // namespace psl

@@ -127,14 +127,19 @@ _C3_ORACLE = {}
 
 
 def _c3_smooth(interp):
-    """721x1440 pole-including mesh, smooth field and ~4-cell smooth velocities, CPU oracle (cached per stencil)."""
+    """721x1440 pole-including mesh, smooth field and ~4-cell smooth velocities; the oracle run by torch on the CPU
+    and on this GPU (cached per stencil), and the difference between the two: the reference's own CPU-vs-CUDA noise."""
     if interp not in _C3_ORACLE:
         H, W, B, V = 721, 1440, 1, 3
         lat, lon = O.make_grids(H, W, True)
         field = O.smooth_field(lat, lon, B, V).float()
         u, v = [t.float() for t in O.smooth_velocity(lat, lon, B, V, 4.0, DT)]
         go = O.smooth_field(lat, lon, B, V, seed=7).float()
-        _C3_ORACLE[interp] = (lat, lon, field, u, v, go, O.sl_advect_fwd_bwd(field, u, v, lat, lon, DT, go, interp))
+        ref_cpu = O.sl_advect_fwd_bwd(field, u, v, lat, lon, DT, go, interp)
+        dev = [t.cuda() for t in (field, u, v, lat, lon, go)]
+        ref_gpu = [t.cpu() for t in O.sl_advect_fwd_bwd(dev[0], dev[1], dev[2], dev[3], dev[4], DT, dev[5], interp)]
+        noise = [relmax(a, b) for a, b in zip(ref_gpu, ref_cpu)]
+        _C3_ORACLE[interp] = (lat, lon, field, u, v, go, ref_cpu, ref_gpu, noise)
     return _C3_ORACLE[interp]
 
 
@@ -143,15 +148,21 @@ def _c3_smooth(interp):
 @pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
 def test_c3_size_values_vs_cpu_oracle(interp, math_mode, cfl):
     """out, grad_field, grad_u, grad_v at 721x1440 (polar rows with 1/cos(lat) reach, cap folds, pole means, both
-    backward paths) against the CPU oracle: north_star tolerances, forward 1e-5, gradients 1e-4 (relative to max)."""
-    lat, lon, field, u, v, go, ref = _c3_smooth(interp)
+    backward paths): north_star tolerances, forward 1e-5, gradients 1e-4 (relative to max).
+    * against the oracle run by torch on this GPU: everywhere;
+    * against the CPU oracle: the forward everywhere; the gradients within 1e-4 or three times the difference
+      between the reference's OWN CPU and CUDA runs, whichever is larger -- next to the poles d(lat)/d(sin lat) =
+      1 / sqrt(1 - s^2) reaches 2e3 and one ulp of libm-vs-libdevice in s moves grad_u / grad_v by 3e-4 of their
+      maximum, which is attained exactly there."""
+    lat, lon, field, u, v, go, ref_cpu, ref_gpu, noise = _c3_smooth(interp)
     got = cuda_fwd_bwd(field, u, v, lat, lon, DT, go, interp, math_mode, cfl=cfl)
-    errs = [relmax(a, b) for a, b in zip(got, ref)]
-    print("c3 smooth", interp, math_mode, cfl, errs)
-    assert errs[0] < 1e-5, errs
-    assert errs[1] < 1e-4, errs
-    # smooth fields: d out / d ix is continuous enough that a cell-edge flip moves grad_u / grad_v by << 1e-4
-    assert errs[2] < 1e-4 and errs[3] < 1e-4, errs
+    e_cpu = [relmax(a, b) for a, b in zip(got, ref_cpu)]
+    e_gpu = [relmax(a, b) for a, b in zip(got, ref_gpu)]
+    print("c3 smooth", interp, math_mode, cfl, "vs cpu", e_cpu, "vs same-gpu torch", e_gpu, "reference cpu-vs-cuda", noise)
+    assert e_gpu[0] < 1e-5 and e_cpu[0] < 1e-5, (e_gpu, e_cpu)
+    assert e_gpu[1] < 1e-4 and e_gpu[2] < 1e-4 and e_gpu[3] < 1e-4, e_gpu
+    for k in (1, 2, 3):
+        assert e_cpu[k] < max(1e-4, 3 * noise[k]), (k, e_cpu, noise)
 
 
 @pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
