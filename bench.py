@@ -6,9 +6,11 @@
 
 A "step" is one forward + one backward of the operator core (model/advection.py:129-169) over
 one batch of synthetic fields.  Workload at N=1: the configuration BASELINE.json's metric is
-quoted on, 0.25 deg (721x1440), 64 channels, batch 1 (SURVEY 8d "C3"); with N>1 the batch is
-sharded (one batch entry per GPU, no data-path collective): weak scaling.  `--decomp latband`
-runs the strong-scaling latitude-band decomposition with NCCL halo exchange instead.
+quoted on, 0.25 deg (721x1440), 64 channels, batch 1 (SURVEY 8d "C3").  With N>1 the SAME global
+problem is split into latitude bands (BASELINE.json configs[2]; strong scaling; halos read in place
+from the neighbours over NVLink peer memory) and the line carries the communication-free
+batch-sharded figure (one replica per GPU, weak scaling) as the extra key `batch_sharded`;
+`--decomp batch` makes the batch-sharded run the headline instead.
 
 Keys beyond the base contract: roofline (dominant kernel), roofline_step (whole step, 44 B per
 grid-pt*ch), cpu_baseline (oracle port timed on the host cores, bounded sample), e2e (host
@@ -45,7 +47,10 @@ def parse():
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--interp", default="bilinear", choices=["bilinear", "bicubic"])
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--decomp", default="batch", choices=["batch", "latband"])
+    ap.add_argument("--decomp", default="auto", choices=["auto", "batch", "latband"],
+                    help="N>1: latitude bands of ONE global problem (strong scaling; default for c3) or one replica "
+                         "per GPU (weak scaling)")
+    ap.add_argument("--no-batch", action="store_true", help="latband: skip the batch-sharded comparison leg")
     ap.add_argument("--no-p2p", action="store_true", help="latband: NCCL transport for the field halo too")
     ap.add_argument("--no-graph", action="store_true", help="latband: eager autograd step instead of a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
@@ -63,14 +68,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel, captured_config):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json); None for any
-    configuration other than the one the capture was taken on (C3, bilinear)."""
+def ncu_traffic(phase, captured_config):
+    """DRAM bytes (read + write) per step of ALL kernels of `phase` ("forward" / "backward"), summed from the committed
+    `ncu --set full` capture of the final kernels (profiles/traffic_r2.json, written by tools/ncu_traffic.py); None for
+    any configuration other than the one the capture was taken on (C3, bilinear, fast math)."""
     if not captured_config:
         return None
-    path = os.path.join(ROOT, "profiles", "traffic.json")
+    path = os.path.join(ROOT, "profiles", "traffic_r2.json")
     try:
-        return json.load(open(path)).get(kernel)
+        return json.load(open(path))["phases"][phase]["dram_bytes"]
     except Exception:
         return None
 
@@ -191,7 +197,10 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if args.decomp == "latband" and world > 1:
+    decomp = args.decomp
+    if decomp == "auto":      # BASELINE.json configs[2]: "0.25 deg ... 1/2/4/8 B200 with latitude-band halo exchange"
+        decomp = "latband" if (world > 1 and args.workload == "c3") else "batch"
+    if decomp == "latband" and world > 1:
         from paradis_model_b200 import halo
         return halo.bench_latband(args, WORKLOADS[args.workload], rank, world, dev)
 
@@ -263,16 +272,24 @@ def run_b200(args):
         return
 
     peak, peak_src = measured_peak()
-    # forward = one kernel (+2 tiny pole kernels); backward = the fused sweep kernel with the two
-    # polar-cap general-path kernels running beside it on side streams (timed together)
-    names = ["sl_fwd_kernel", "sl_bwd_sweep_kernel"]
+    # forward = pole_means + sl_fwd_kernel + pole_rows_fix; backward = 2 x pole_means + rows_prep + the row-sweep
+    # kernel (all latitudes) + guard / pole fix-ups + the three (normally empty) launches of the fallback path.
+    # Both phases are timed with CUDA events on the launching stream; `traffic` sums the DRAM bytes of every
+    # kernel of the phase from the committed ncu capture.
+    bilinear = args.interp == "bilinear"
+    names = ["sl_fwd_kernel", "sl_bwd_rows_kernel" if bilinear else "sl_bwd_sweep_kernel"]
+    phase_names = ["forward", "backward"]
     alg = [BYTES_FWD, BYTES_BWD]
     dom = max(range(2), key=lambda i: phase[i])
     achieved = alg[dom] * pts_rank / (phase[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(names[dom], args.workload == "c3" and args.interp == "bilinear"), "peak_source": peak_src,
+    captured = args.workload == "c3" and bilinear and args.math == "fast"
+    roofline = {"bound": "hbm", "kernel": names[dom], "phase": phase_names[dom] + " (all kernels of the phase)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(phase_names[dom], captured), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom] * pts_rank, "ms_per_launch": phase[dom],
-                "phases_ms": dict(zip(names, phase))}
+                "phases_ms": dict(zip(phase_names, phase)),
+                "phases_frac": {n: alg[i] * pts_rank / (phase[i] * 1e-3) / 1e9 / peak for i, n in enumerate(phase_names)},
+                "phases_traffic": {n: ncu_traffic(n, captured) for n in phase_names}}
     step_gbs = BYTES_STEP * pts_rank / (ms_step * 1e-3) / 1e9
     line = {"metric": "SL advection fwd+bwd grid-pts*ch/s", "value": world * pts_rank / (ms_step * 1e-3),
             "unit": "grid-pt*ch/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -286,7 +303,7 @@ def run_b200(args):
             "roofline": roofline,
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                               "bytes_per_unit": BYTES_STEP, "frac_of_8TBs": step_gbs / 8000.0},
-            "clocks": clocks, "gpu_launches": 15 * args.steps, "wall_ms_timed_region": wall_ms}
+            "clocks": clocks, "gpu_launches": (12 if bilinear else 15) * args.steps, "wall_ms_timed_region": wall_ms}
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:

@@ -199,9 +199,11 @@ template <bool EXACT, int INTERP, int VEC, bool PEER>
 __global__ void __launch_bounds__(256) sl_bwd_arrival_kernel(const Params P) {
   const int c = blockIdx.y, b = blockIdx.z, pl = b * P.V + c;
   if (P.plane_filter && !P.plane_filter[pl]) return;   // uniform per block
-  const unsigned unit = blockIdx.x * blockDim.x + threadIdx.x;
   int reach = 0;
-  if (unit < (unsigned)(P.it_arrN * P.upr)) {
+  // grid-stride over the units of the plane: the fallback launch behind the row sweep (plane_filter set, almost
+  // always nothing to do) runs a handful of blocks per plane instead of one per 256 units
+  for (unsigned unit = blockIdx.x * blockDim.x + threadIdx.x; unit < (unsigned)(P.it_arrN * P.upr);
+       unit += gridDim.x * blockDim.x) {
     const unsigned r = P.w4_mul ? fast_div(unit, P.w4_mul, P.w4_shift) : unit / (unsigned)P.upr;
     const int x = (unit - r * P.upr) * VEC;
     const int y = P.it_arr0 + (int)r;  // global arrival row
@@ -606,6 +608,7 @@ static int fill_params(Params& P, const paradis_sl_geom* g, int B, int V, float 
   P.Cx = (float)((double)p - (double)g->min_lon * (double)P.Ax);
   P.Cy = (float)((double)p - (double)g->min_lat * (double)P.Ay);
   P.clamp_lo = (float)(-1 + 1e-7); P.clamp_hi = (float)(1 - 1e-7);
+  P.Wf = (float)g->W; P.ix_wrap = (float)(g->W + p);
   P.B = B; P.V = V; P.pole_fix = pole_fix ? 1 : 0;
   {  // rows (global, of tap row 0) whose whole stencil is plain field data inside the window
     const int nt = interp == 1 ? 2 : 4;
@@ -726,6 +729,7 @@ static int launch_general(Params P, int vec, cudaStream_t st, bool want_field, i
   set_units(P, vec, P.it_arrN);
   const unsigned units = (unsigned)P.it_arrN * P.upr;
   dim3 grid((units + 255) / 256, P.V, P.B);
+  if (P.plane_filter && grid.x > 8) grid.x = 8;       // see the grid-stride loop of the arrival kernel
   if ((int)grid.x > max_nblk) return fail(PARADIS_ERR_WORKSPACE, "internal: blkmax layout");
   P.nblk = grid.x;
   if (phases & PARADIS_BWD_ARRIVAL) {

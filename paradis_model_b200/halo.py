@@ -85,20 +85,23 @@ def band_rows(H: int, world: int, cost: Optional[List[float]] = None) -> List[Tu
     return out
 
 
-def row_costs(H: int, W: int, cfl_cells: float, cap_cost: float = 2.8) -> List[float]:
-    """Relative backward cost of a row on a pole-to-pole mesh: rows whose longitudinal reach exceeds the
-    sweep's 32-column halo go through the general gather (measured ~2.8x a swept row)."""
+def row_costs(H: int, W: int, cfl_cells: float, strip: int = 288, base: float = 6.0) -> List[float]:
+    """Relative backward cost of a row on a pole-to-pole mesh, the model the row-sweep kernel balances its own CTAs
+    with (csrc/paradis_sl.cu, launch_rows): a constant for the producers plus the number of 32-record steps a
+    consumer scans for the row -- its strip plus the longitudinal reach of the row either side, which grows as
+    1 / cos(lat) and becomes the whole circle next to the poles."""
     dphi = math.pi / max(H - 1, 1)
     delta = cfl_cells * dphi
     out = []
     for i in range(H):
         lat = abs(-math.pi / 2 + i * dphi) + delta
-        cells = 1 << 20
+        cells = W
         if lat < math.pi / 2 - 1e-9:
             sdl = math.sin(delta) / math.cos(lat)
             if sdl < 1.0:
-                cells = math.asin(sdl) / (2 * math.pi / W) + 4
-        out.append(cap_cost if cells > 32 else 1.0 + 0.25 * (cells > 16))
+                cells = min(W, math.asin(sdl) / (2 * math.pi / W) + 4)
+        scan = min(W, strip + 2 * cells)
+        out.append(base + math.ceil(scan / 32))
     return out
 
 
@@ -339,35 +342,146 @@ def bench_latband(args, workload, rank, world, dev):
         except Exception as exc:
             mode += f" (graph capture unavailable: {type(exc).__name__}: {exc})"[:200]
 
+    from bench import BYTES_FWD, BYTES_BWD, ClockSampler
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
     dist.barrier()
+    sampler = ClockSampler(dev.index if dev.index is not None else 0)
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop()
     dist.barrier()
     P.check_status(dev)
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
+
+    # ---- the two phases of a band, timed separately on every rank (eager C-ABI calls; max over ranks)
+    from .ops import RawAdvection
+    own, ext = plan.windows()
+    if peer is not None:
+        Rf = RawAdvection(geo.band(own, own, own, peer.peer()), Bg, V, args.interp, True, args.math, CFL_CELLS)
+        Rb = RawAdvection(geo.band(own, ext, own, peer.peer(), peer.arr_peer()), Bg, V, args.interp, True, args.math,
+                          CFL_CELLS)
+        phase = []
+        for fn, pub in ((lambda: Rf.forward(field, u, v, dt), lambda: peer.publish(field)),
+                        (lambda: Rb.backward(go, field, u, v, dt, 3), lambda: peer.publish_backward(field, u, v, go))):
+            pub(); fn()
+            torch.cuda.synchronize(); dist.barrier()
+            n_ph = max(3, min(args.steps, 10))
+            acc = 0.0
+            for _ in range(n_ph):
+                pub()                                    # publishes and barriers outside the timed kernel phase
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                acc += a.elapsed_time(b)
+            tp = torch.tensor([acc / n_ph], device=dev)
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            phase.append(float(tp.item()))
+    else:
+        phase = [float("nan"), float("nan")]
+
+    # ---- end to end through the public API: pinned host bands -> H2D -> lat_band_advect fwd + bwd -> D2H
+    e2e = None
+    if not getattr(args, "no_e2e", False):
+        h_in = [t.cpu().pin_memory() for t in (field, u, v, go)]
+        h_out = [torch.empty_like(h_in[0]).pin_memory() for _ in range(4)]
+
+        def e2e_step():
+            f, uu, vv, g = [t.to(dev, non_blocking=True) for t in h_in]
+            f.requires_grad_(True); uu.requires_grad_(True); vv.requires_grad_(True)
+            out = lat_band_advect(f, uu, vv, geo, plan, dt, args.interp, True, args.math, CFL_CELLS, None, peer)
+            out.backward(g)
+            for dst, src in zip(h_out, (out.detach(), f.grad, uu.grad, vv.grad)):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        dist.barrier()
+        n_e2e = max(2, min(args.steps, 5))
+        import time as _time
+        t0 = _time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        te = torch.tensor([(_time.perf_counter() - t0) / n_e2e], device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        band_bytes = torch.tensor([4 * field.numel() * 4], device=dev, dtype=torch.float64)
+        dist.all_reduce(band_bytes)
+        e2e = {"value": Bg * V * H * W / float(te.item()), "unit": "grid-pt*ch/s",
+               "h2d_bytes_per_step": int(band_bytes.item()), "d2h_bytes_per_step": int(band_bytes.item()),
+               "ms_per_step": float(te.item()) * 1e3, "steps": n_e2e,
+               "api": "paradis_model_b200.halo.lat_band_advect (autograd) on pinned host bands, all ranks, bytes summed over ranks"}
+
+    # ---- the communication-free alternative in the same run: every rank a full replica (batch-sharded, weak scaling)
+    batch = None
+    if not getattr(args, "no_batch", False):
+        full_d = [t.to(dev) for t in S.white_noise_inputs(H, W, Bg, V, dt, seed=rank)]
+        Rr = RawAdvection(geo, Bg, V, args.interp, True, args.math, CFL_CELLS)
+
+        def rstep():
+            Rr.forward(full_d[0], full_d[1], full_d[2], dt)
+            Rr.backward(full_d[3], full_d[0], full_d[1], full_d[2], dt, 3)
+
+        for _ in range(3):
+            rstep()
+        torch.cuda.synchronize(); dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nb = max(3, min(args.steps, 20))
+        a.record()
+        for _ in range(nb):
+            rstep()
+        b.record()
+        torch.cuda.synchronize(); dist.barrier()
+        tb = torch.tensor([a.elapsed_time(b) / nb], device=dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        batch = {"value": world * Bg * V * H * W / (float(tb.item()) * 1e-3), "unit": "grid-pt*ch/s",
+                 "ms_per_step": float(tb.item()), "scaling": "weak",
+                 "parallelism": f"batch-sharded x{world}: one full {H}x{W} replica per GPU, no communication"}
+        del full_d, Rr
+
     if rank == 0:
         pts = Bg * V * H * W
         peak, src = measured_peak()
         gbs = BYTES_STEP * pts / (ms_step * 1e-3) / 1e9
         halo_bytes = 2 * plan.halo * W * V * Bg * 4
-        print(json.dumps({
+        dom = 1 if not (phase[1] != phase[1]) and phase[1] >= phase[0] else 0
+        names = ["sl_fwd_kernel", "sl_bwd_rows_kernel" if args.interp == "bilinear" else "sl_bwd_sweep_kernel"]
+        alg = [BYTES_FWD, BYTES_BWD]
+        band_pts = pts / world                                   # max-over-ranks time against the mean band
+        ach = alg[dom] * band_pts / (phase[dom] * 1e-3) / 1e9 if phase[dom] == phase[dom] else None
+        line = {
             "metric": "SL advection fwd+bwd grid-pts*ch/s", "value": pts / (ms_step * 1e-3), "unit": "grid-pt*ch/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {H}x{W} mesh, V={V}, batch {Bg} GLOBAL, {args.interp}, "
-                                   f"latitude bands x{world}, halo {plan.halo} rows",
+            "config": {"workload": f"{args.workload}: {H}x{W} mesh, V={V}, batch {Bg} GLOBAL (the N=1 problem), {args.interp}, "
+                                   f"math={args.math}, pole_fix, cfl_cells={CFL_CELLS}, latitude bands x{world}, halo {plan.halo} rows",
+                       "inputs": "field~N(0,1); u,v~N(0,(2 cells)^2) clipped at +-4 cells; grad_out~N(0,1); seed 0, same global tensors for every N",
+                       "l2": "per-rank inputs exceed the 126 MB L2 up to N=8 (133 MB per rank there); no flush",
                        "parallelism": f"latband{world} (cost-balanced bands, rank 0 owns {plan.rows} rows): {transport}; "
                                       f"{halo_bytes} B of halo per rank per tensor",
                        "launch": mode},
+            "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": src,
+                         "algorithmic_bytes_per_launch": alg[dom] * band_pts, "ms_per_launch": phase[dom],
+                         "phases_ms": dict(zip(["forward", "backward"], phase)),
+                         "note": "per-GPU figures of one band: slowest rank's phase time against the mean band size"},
             "roofline_step": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
-                              "frac": gbs / (peak * world), "peak_source": src}}), flush=True)
+                              "frac": gbs / (peak * world), "peak_source": src},
+            "collective": {"kind": "none (NCCL is only used for rendezvous and the timing all-reduce)" if peer is not None
+                           else "NCCL send/recv (batch_isend_irecv)",
+                           "data_path": transport, "halo_bytes_per_rank_per_tensor": halo_bytes,
+                           "barriers_per_step": 4 if peer is not None else 0},
+            "clocks": clocks, "gpu_launches": 12 * args.steps}
+        if e2e:
+            line["e2e"] = e2e
+        if batch:
+            line["batch_sharded"] = batch
+        print(json.dumps(line), flush=True)
     dist.destroy_process_group()
