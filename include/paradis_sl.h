@@ -124,6 +124,10 @@ int paradis_geocyclic_dwconv_bwd_weight(const float* x, const float* gy, float* 
                                         int B, int C, int H, int W, int k, void* workspace,
                                         size_t workspace_bytes, void* stream);
 
+/* PhysicalDownsample (model/blocks.py:57-71): GeoCyclic pad 2 + AvgPool2d(kernel 5, stride) in one kernel that only
+ * computes the strided outputs.  x [B, C, H, W] -> y [B, C, (H - 1) / stride + 1, (W - 1) / stride + 1]. */
+int paradis_geocyclic_avgpool5_fwd(const float* x, float* y, int B, int C, int H, int W, int stride, void* stream);
+
 /* ---- Semi-Lagrangian advection core: model/advection.py:129-169 --------------------
  * (pole mean -> rotated-pole backtrack -> pixel coords -> GeoCyclic pad -> grid_sample
  *  -> pole mean), fused.

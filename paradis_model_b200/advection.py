@@ -6,6 +6,14 @@ Constructor and ``forward(hidden_features, u, v, dt)`` keep the reference's sign
 ``strict=True`` and ``model/paradis.py`` runs unmodified on top of it.  Lines 129-169 of the
 reference (pole mean, departure points, padding, grid_sample, pole mean) run as ONE fused
 CUDA operator, ``torch.ops.paradis.sl_advect``.
+
+Displacement limits.  The reference puts no bound on the velocities.  Here the forward accepts any displacement; the
+deterministic adjoint tracks row displacements of up to 126 latitude rows (`PARADIS_SL_MAX_DISP_ROWS`).  A larger one --
+or, in a latitude-band call, a departure stencil outside the band's halo -- is reported, not ignored: the kernel stores
+an error code in a host-mapped status word which every later call of the operator checks on entry
+(`RuntimeError: paradis_sl device status DISPLACEMENT`), and `paradis_model_b200.check_status()` checks it
+synchronously.  `cfl_cells` is only a speed hint for the fused backward: planes that exceed it are recomputed by the
+general path on the device.
 """
 import torch
 
@@ -77,13 +85,6 @@ class NeuralSemiLagrangian(torch.nn.Module):
     def geometry(self) -> SLGeometry:
         H, W = self.mesh_size
         return SLGeometry(self.sl_tables, self._scalars, H, W)
-
-    def enforce_pole_continuity(self, x):
-        """Reference helper (advection.py:100-114); the fused op applies it internally."""
-        x_fixed = x.clone()
-        x_fixed[:, :, 0, :] = x[:, :, 0:1, :].mean(dim=3, keepdim=True).squeeze(-1)
-        x_fixed[:, :, -1, :] = x[:, :, -1:, :].mean(dim=3, keepdim=True).squeeze(-1)
-        return x_fixed
 
     def forward(self, hidden_features: torch.Tensor, u: torch.Tensor, v: torch.Tensor, dt: float) -> torch.Tensor:
         """Compute advection using rotated coordinate system."""

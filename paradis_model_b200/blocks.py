@@ -5,7 +5,7 @@ the padded tensor is never materialised.  Parameter names match the reference (s
 import torch
 from torch import nn
 
-from .ops import geocyclic_dwconv
+from .ops import geocyclic_avgpool5, geocyclic_dwconv
 from .padding import GeoCyclicPadding
 
 
@@ -27,20 +27,27 @@ class SepConv(nn.Module):
         return self.pointwise(x)
 
 
+class CLinear(nn.Module):
+    """1x1 convolution (model/blocks.py:74-89); stays cuDNN."""
+
+    def __init__(self, input_dim, output_dim, mesh_size, kernel_size=1, bias=True):
+        super().__init__()
+        self.conv = nn.Conv2d(input_dim, output_dim, kernel_size=1, bias=bias)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
 class PhysicalDownsample(nn.Module):
-    """GeoCyclic pad 2 + 5x5 average pooling with `stride` (blocks.py:57-71).  The pooling has no padding of
-    its own, so it is the 5x5 box filter of the GeoCyclic-padded field sampled every `stride` points: one
-    fused depthwise convolution with constant taps 1/25."""
+    """GeoCyclic pad 2 + 5x5 average pooling with `stride` (blocks.py:57-71) as one kernel that computes only the
+    strided outputs (`paradis::geocyclic_avgpool5`)."""
 
     def __init__(self, stride=4):
         super().__init__()
         # both kept for structural parity with the reference (the fused kernel replaces them in forward)
         self.pool = nn.AvgPool2d(kernel_size=5, stride=stride, count_include_pad=False)
         self.padding = GeoCyclicPadding(2)
-        self.register_buffer("_box", torch.full((1, 1, 5, 5), 1.0 / 25.0), persistent=False)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        C = x.shape[1]
-        y = geocyclic_dwconv(x, self._box.expand(C, 1, 5, 5).contiguous())
         s = self.pool.stride if isinstance(self.pool.stride, int) else self.pool.stride[0]
-        return y if s == 1 else y[:, :, ::s, ::s].contiguous()
+        return geocyclic_avgpool5(x, s)

@@ -17,6 +17,8 @@
 
 #include "../../include/paradis_sl.h"
 
+void psl_set_error(const char* msg);   // paradis_sl.cu: the calling thread's paradis_last_error() string
+
 namespace {
 
 constexpr int TW = 32, TH = 32, RPT = 4;   // tile 32 x 32 outputs, 256 threads, 4 vertically adjacent outputs each
@@ -182,12 +184,20 @@ __global__ void geo_dwconv_wgrad_reduce_kernel(const float* __restrict__ partial
   else if (gbias) gbias[c] = s;
 }
 
+int err(int code, const char* msg) {
+  psl_set_error(msg);
+  return code;
+}
+
 int check(const void* a, const void* b, int B, int C, int H, int W, int k) {
-  if (!a || !b) return PARADIS_ERR_NULL_POINTER;
-  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return PARADIS_ERR_BAD_SHAPE;
-  if (W % 2) return PARADIS_ERR_ODD_WIDTH;
-  if (k != 3 && k != 5 && k != 7) return PARADIS_ERR_BAD_INTERP;
-  if (H < (k - 1) / 2 + 2 || W < k - 1 || (long long)B * C > 65535) return PARADIS_ERR_BAD_SHAPE;
+  if (!a || !b) return err(PARADIS_ERR_NULL_POINTER, "geocyclic_dwconv: NULL tensor pointer");
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return err(PARADIS_ERR_BAD_SHAPE, "geocyclic_dwconv: non-positive dimension");
+  if (W % 2) return err(PARADIS_ERR_ODD_WIDTH, "Number of longitude points must be even");
+  if (k != 3 && k != 5 && k != 7) return err(PARADIS_ERR_BAD_INTERP, "geocyclic_dwconv: kernel size must be 3, 5 or 7");
+  // H >= 2P + 2: the north and the south cap never fold onto the same row (the cap kernel of the backward adds one
+  // fold per block, see geo_dwconv_bwd_caps_kernel)
+  if (H < k + 1 || W < k - 1) return err(PARADIS_ERR_BAD_SHAPE, "geocyclic_dwconv: mesh too small for the kernel size (H >= k + 1, W >= k - 1)");
+  if ((long long)B * C > 65535) return err(PARADIS_ERR_BAD_SHAPE, "geocyclic_dwconv: B*C exceeds 65535 planes per call");
   return PARADIS_OK;
 }
 
@@ -204,7 +214,8 @@ int run(int what, const float* a, const float* w, const float* bias, float* out,
     geo_dwconv_wgrad_kernel<K><<<grid, 256, 0, st>>>(a, w /* = gy */, ws, C, H, W);
     geo_dwconv_wgrad_reduce_kernel<<<C, 64, 0, st>>>(ws, out, out2, B, C, grid.x * grid.y, K * K + 1);
   }
-  return cudaGetLastError() == cudaSuccess ? PARADIS_OK : PARADIS_ERR_CUDA;
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PARADIS_OK : err(PARADIS_ERR_CUDA, cudaGetErrorString(e));
 }
 
 int dispatch(int what, const float* a, const float* w, const float* bias, float* out, float* out2, float* ws, int B,
@@ -215,19 +226,51 @@ int dispatch(int what, const float* a, const float* w, const float* bias, float*
   return run<7>(what, a, w, bias, out, out2, ws, B, C, H, W, st);
 }
 
+
+// PhysicalDownsample (model/blocks.py:57-71): GeoCyclic pad 2 + AvgPool2d(5, stride) = the 5x5 box mean of the padded
+// field at every stride-th point.  One thread per OUTPUT point: only Ho x Wo values are computed and written (the
+// round-1 version ran the full-resolution depthwise kernel and discarded all but 1 / stride^2 of it).
+__global__ void geo_avgpool5_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int Ho, int Wo,
+                                    int stride) {
+  const long long pl = blockIdx.z;
+  const int io = blockIdx.y, jo = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jo >= Wo) return;
+  const float* xp = x + pl * (long long)H * W;
+  const int halfW = W >> 1;
+  float s = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    int i = io * stride + a - 2, shift = 0;         // unpadded row of the tap
+    if (i < 0) { i = -i; shift = halfW; }
+    else if (i >= H) { i = 2 * (H - 1) - i; shift = halfW; }
+    const float* row = xp + (long long)i * W;
+    float r = 0.0f;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      int j = jo * stride + b - 2 - shift;
+      if (j < 0) j += W;
+      if (j < 0) j += W;
+      if (j >= W) j -= W;
+      r += __ldg(row + j);
+    }
+    s += r;
+  }
+  y[(pl * Ho + io) * Wo + jo] = s * (1.0f / 25.0f);
+}
+
 }  // namespace
 
 extern "C" int paradis_geocyclic_dwconv_fwd(const float* x, const float* weight, const float* bias, float* y, int B,
                                             int C, int H, int W, int k, void* stream) {
   if (int rc = check(x, y, B, C, H, W, k)) return rc;
-  if (!weight) return PARADIS_ERR_NULL_POINTER;
+  if (!weight) return err(PARADIS_ERR_NULL_POINTER, "geocyclic_dwconv: weight is NULL");
   return dispatch(0, x, weight, bias, y, nullptr, nullptr, B, C, H, W, k, stream);
 }
 
 extern "C" int paradis_geocyclic_dwconv_bwd_input(const float* gy, const float* weight, float* gx, int B, int C, int H,
                                                   int W, int k, void* stream) {
   if (int rc = check(gy, gx, B, C, H, W, k)) return rc;
-  if (!weight) return PARADIS_ERR_NULL_POINTER;
+  if (!weight) return err(PARADIS_ERR_NULL_POINTER, "geocyclic_dwconv: weight is NULL");
   return dispatch(1, gy, weight, nullptr, gx, nullptr, nullptr, B, C, H, W, k, stream);
 }
 
@@ -240,7 +283,18 @@ extern "C" int paradis_geocyclic_dwconv_bwd_weight(const float* x, const float* 
                                                    int B, int C, int H, int W, int k, void* workspace,
                                                    size_t workspace_bytes, void* stream) {
   if (int rc = check(x, gy, B, C, H, W, k)) return rc;
-  if (!gweight) return PARADIS_ERR_NULL_POINTER;
-  if (!workspace || workspace_bytes < paradis_geocyclic_dwconv_wgrad_workspace(B, C, H, W, k)) return PARADIS_ERR_WORKSPACE;
+  if (!gweight) return err(PARADIS_ERR_NULL_POINTER, "geocyclic_dwconv: grad weight is NULL");
+  if (!workspace || workspace_bytes < paradis_geocyclic_dwconv_wgrad_workspace(B, C, H, W, k))
+    return err(PARADIS_ERR_WORKSPACE, "geocyclic_dwconv: weight-gradient workspace too small");
   return dispatch(2, x, gy, nullptr, gweight, gbias, (float*)workspace, B, C, H, W, k, stream);
+}
+
+extern "C" int paradis_geocyclic_avgpool5_fwd(const float* x, float* y, int B, int C, int H, int W, int stride, void* stream) {
+  if (int rc = check(x, y, B, C, H, W, 5)) return rc;
+  if (stride < 1) return err(PARADIS_ERR_BAD_SHAPE, "geocyclic_avgpool5: stride must be >= 1");
+  const int Ho = (H + 4 - 5) / stride + 1, Wo = (W + 4 - 5) / stride + 1;     // AvgPool2d(5, stride) of the padded plane
+  dim3 grid((Wo + 127) / 128, Ho, B * C);
+  geo_avgpool5_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, H, W, Ho, Wo, stride);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PARADIS_OK : err(PARADIS_ERR_CUDA, cudaGetErrorString(e));
 }

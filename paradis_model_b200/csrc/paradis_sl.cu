@@ -40,6 +40,8 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+void psl_set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }   // for geo_dwconv.cu
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PARADIS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -827,11 +829,11 @@ static bool plan_sweep(const Params& P, float cfl_cells, int planes, int capacit
   {
     int i = lo; double accum = 0.0;
     for (int k = 0; k < nb; ++k) {
-      S.ra[k] = (short)i;
+      S.ra[k] = i;
       const double goal = total * (k + 1) / nb;
       while (i < hi && (accum + row_cost(i) <= goal || i == S.ra[k])) { accum += row_cost(i); ++i; }
       if (k == nb - 1) i = hi;
-      S.rb[k] = (short)i;
+      S.rb[k] = i;
     }
   }
   S.nstrips = nstrips; S.wc = wc; S.rr = rr; S.ring = 2 * rr + NT; S.pitch = sweep_pitch(wc);

@@ -71,7 +71,7 @@ struct SweepPlan {
   int nbands, nstrips, wc, rr, ring, pitch;   // pitch = sweep_pitch(wc)
   int planes;
   ReachModel reach;
-  short ra[kMaxBands], rb[kMaxBands];         // band k owns destination rows [ra[k], rb[k]); bands are
+  int ra[kMaxBands], rb[kMaxBands];           // band k owns destination rows [ra[k], rb[k]); bands are
                                               // sorted by decreasing cost
   unsigned char* plane_flag;                  // [planes] set to 1 on a contract violation
   int out0, outN;                             // rows held by the output tensors (global first row, count)

@@ -21,7 +21,8 @@ from torch import Tensor
 
 from . import _lib
 
-__all__ = ["SLGeometry", "sl_advect", "geocyclic_pad", "geocyclic_dwconv", "check_status", "host_fwd_bwd"]
+__all__ = ["SLGeometry", "sl_advect", "geocyclic_pad", "geocyclic_dwconv", "geocyclic_avgpool5", "check_status",
+           "poll_status", "host_fwd_bwd"]
 
 _status_words: dict = {}
 
@@ -203,6 +204,9 @@ def _sl_advect(field: Tensor, u: Tensor, v: Tensor, tables: Tensor, scalars: Lis
                interp: int, pole_fix: bool, math: int, windows: List[int], cfl: float) -> Tensor:
     B, V, H, W, ownN, arrN = _check_inputs(field, u, v, windows)
     L = _lib.lib()
+    if field.dtype == torch.float64 or u.dtype == torch.float64 or v.dtype == torch.float64:
+        raise RuntimeError("paradis::sl_advect computes in fp32 (like the reference under its fp32 / bf16-mixed settings); "
+                           "float64 inputs would silently lose precision -- cast them explicitly")
     poll_status(field.device)
     if tables.device != field.device:
         raise RuntimeError(f"paradis::sl_advect: geometry tables live on {tables.device}, the tensors on {field.device}; "
@@ -409,29 +413,39 @@ def _(x, weight, bias):
 
 
 @torch.library.custom_op("paradis::geocyclic_dwconv_backward", mutates_args=(), device_types="cuda")
-def _geocyclic_dwconv_backward(gy: Tensor, x: Tensor, weight: Tensor, need_bias: bool) -> Tuple[Tensor, Tensor, Tensor]:
+def _geocyclic_dwconv_backward(gy: Tensor, x: Tensor, weight: Tensor, need_input: bool, need_weight: bool,
+                               need_bias: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """Only the requested gradients are computed (a constant filter, e.g. the box of PhysicalDownsample, skips the
+    weight-gradient pass and its workspace)."""
     B, Cn, H, W = x.shape
     k = weight.shape[-1]
     L = _lib.lib()
-    gyf, xf, wf = gy.float().contiguous(), x.float().contiguous(), weight.float().contiguous()
-    gx = torch.empty_like(xf)
-    gw = torch.empty_like(wf)
-    gb = torch.empty(Cn if need_bias else 0, dtype=torch.float32, device=x.device)
-    ws_bytes = L.paradis_geocyclic_dwconv_wgrad_workspace(B, Cn, H, W, k)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    gyf, wf = gy.float().contiguous(), weight.float().contiguous()
+    empty = lambda: torch.empty(0, dtype=torch.float32, device=x.device)
+    gx, gw, gb = empty(), empty(), empty()
     with torch.cuda.device(x.device):
-        rc = L.paradis_geocyclic_dwconv_bwd_input(_ptr(gyf), _ptr(wf), _ptr(gx), B, Cn, H, W, k, _stream(x))
-        _lib.check(rc, "paradis_geocyclic_dwconv_bwd_input")
-        rc = L.paradis_geocyclic_dwconv_bwd_weight(_ptr(xf), _ptr(gyf), _ptr(gw), _ptr(gb) if need_bias else _ptr(None),
-                                                   B, Cn, H, W, k, _ptr(ws), ws_bytes, _stream(x))
-        _lib.check(rc, "paradis_geocyclic_dwconv_bwd_weight")
+        if need_input:
+            gx = torch.empty((B, Cn, H, W), dtype=torch.float32, device=x.device)
+            rc = L.paradis_geocyclic_dwconv_bwd_input(_ptr(gyf), _ptr(wf), _ptr(gx), B, Cn, H, W, k, _stream(x))
+            _lib.check(rc, "paradis_geocyclic_dwconv_bwd_input")
+        if need_weight or need_bias:
+            xf = x.float().contiguous()
+            gw = torch.empty_like(wf)
+            gb = torch.empty(Cn if need_bias else 0, dtype=torch.float32, device=x.device)
+            ws_bytes = L.paradis_geocyclic_dwconv_wgrad_workspace(B, Cn, H, W, k)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            rc = L.paradis_geocyclic_dwconv_bwd_weight(_ptr(xf), _ptr(gyf), _ptr(gw), _ptr(gb) if need_bias else _ptr(None),
+                                                       B, Cn, H, W, k, _ptr(ws), ws_bytes, _stream(x))
+            _lib.check(rc, "paradis_geocyclic_dwconv_bwd_weight")
     return gx, gw, gb
 
 
 @_geocyclic_dwconv_backward.register_fake
-def _(gy, x, weight, need_bias):
-    return torch.empty_like(x, dtype=torch.float32), torch.empty_like(weight, dtype=torch.float32), \
-        x.new_empty((x.shape[1] if need_bias else 0,), dtype=torch.float32)
+def _(gy, x, weight, need_input, need_weight, need_bias):
+    none = lambda: x.new_empty((0,), dtype=torch.float32)
+    return (torch.empty_like(x, dtype=torch.float32) if need_input else none(),
+            torch.empty_like(weight, dtype=torch.float32) if (need_weight or need_bias) else none(),
+            x.new_empty((x.shape[1],), dtype=torch.float32) if need_bias else none())
 
 
 def _dw_setup(ctx, inputs, output):
@@ -443,11 +457,62 @@ def _dw_setup(ctx, inputs, output):
 
 def _dw_backward(ctx, gy):
     x, weight = ctx.saved_tensors
-    gx, gw, gb = torch.ops.paradis.geocyclic_dwconv_backward(gy, x, weight, ctx.has_bias)
-    return gx.to(ctx.dtypes[0]), gw.to(ctx.dtypes[1]), (gb.to(ctx.dtypes[2]) if ctx.has_bias else None)
+    need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    need_b = ctx.has_bias and ctx.needs_input_grad[2]
+    if not (need_x or need_w or need_b):
+        return None, None, None
+    gx, gw, gb = torch.ops.paradis.geocyclic_dwconv_backward(gy, x, weight, need_x, need_w, need_b)
+    return (gx.to(ctx.dtypes[0]) if need_x else None, gw.to(ctx.dtypes[1]) if need_w else None,
+            gb.to(ctx.dtypes[2]) if need_b else None)
 
 
 _geocyclic_dwconv.register_autograd(_dw_backward, setup_context=_dw_setup)
+
+
+# --------------------------------------------------------------------------------------
+# geocyclic_avgpool5: PhysicalDownsample (blocks.py:57-71), strided outputs only
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("paradis::geocyclic_avgpool5", mutates_args=(), device_types="cuda")
+def _geocyclic_avgpool5(x: Tensor, stride: int) -> Tensor:
+    B, Cn, H, W = x.shape
+    xf = x.float().contiguous()
+    y = torch.empty((B, Cn, (H - 1) // stride + 1, (W - 1) // stride + 1), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().paradis_geocyclic_avgpool5_fwd(_ptr(xf), _ptr(y), B, Cn, H, W, stride, _stream(x))
+    _lib.check(rc, "paradis_geocyclic_avgpool5_fwd")
+    return y.to(x.dtype)
+
+
+@_geocyclic_avgpool5.register_fake
+def _(x, stride):
+    B, Cn, H, W = x.shape
+    return x.new_empty((B, Cn, (H - 1) // stride + 1, (W - 1) // stride + 1))
+
+
+def _pool_setup(ctx, inputs, output):
+    x, stride = inputs
+    ctx.stride, ctx.shape, ctx.dtype = stride, tuple(x.shape), x.dtype
+
+
+def _pool_backward(ctx, gy):
+    # adjoint = the box filter's input gradient applied to grad_y scattered back onto the full-resolution mesh
+    B, Cn, H, W = ctx.shape
+    s = ctx.stride
+    g_full = torch.zeros((B, Cn, H, W), dtype=torch.float32, device=gy.device)
+    g_full[:, :, ::s, ::s] = gy.float()
+    box = torch.full((Cn, 1, 5, 5), 1.0 / 25.0, dtype=torch.float32, device=gy.device)
+    gx, _, _ = torch.ops.paradis.geocyclic_dwconv_backward(g_full, g_full, box, True, False, False)
+    return gx.to(ctx.dtype), None
+
+
+_geocyclic_avgpool5.register_autograd(_pool_backward, setup_context=_pool_setup)
+
+
+def geocyclic_avgpool5(x: Tensor, stride: int) -> Tensor:
+    """``AvgPool2d(5, stride)(GeoCyclicPadding(2)(x))`` (model/blocks.py:57-71) in one kernel."""
+    assert x.dim() == 4, "Input must be 4-dimensional [batch, channels, lat, lon]"
+    assert x.shape[3] % 2 == 0, "Number of longitude points must be even"
+    return torch.ops.paradis.geocyclic_avgpool5(x, int(stride))
 
 
 def geocyclic_dwconv(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:

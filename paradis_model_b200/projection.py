@@ -11,36 +11,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
-from .padding import GeoCyclicPadding
-
-
-class CLinear(nn.Module):
-    """1x1 convolution (model/blocks.py:74-89)."""
-
-    def __init__(self, input_dim, output_dim, mesh_size, kernel_size=1, bias=True):
-        super().__init__()
-        self.conv = nn.Conv2d(input_dim, output_dim, kernel_size=1, bias=bias)
-
-    def forward(self, x):
-        return self.conv(x)
-
-
-class SepConv(nn.Module):
-    """GeoCyclic pad + depthwise k x k + pointwise 1x1 (model/blocks.py:92-116)."""
-
-    def __init__(self, input_dim, output_dim, mesh_size, kernel_size=3, bias=True):
-        super().__init__()
-        self.padding = (kernel_size - 1) // 2
-        self.geo_padding = GeoCyclicPadding(self.padding)
-        self.depthwise = nn.Conv2d(input_dim, input_dim, kernel_size, groups=input_dim, bias=False)
-        self.pointwise = nn.Conv2d(input_dim, output_dim, kernel_size=1, bias=bias)
-
-    def forward(self, x):
-        k = self.depthwise.kernel_size[0]
-        if x.is_cuda and k in (3, 5, 7) and self.depthwise.bias is None:
-            from .ops import geocyclic_dwconv     # padding fused into the depthwise convolution
-            return self.pointwise(geocyclic_dwconv(x, self.depthwise.weight))
-        return self.pointwise(self.depthwise(self.geo_padding(x)))
+from .blocks import CLinear, SepConv        # one definition of each layer (blocks.py)
 
 
 _LAYERS = {"SepConv": SepConv, "CLinear": CLinear}

@@ -738,3 +738,28 @@ def test_faster_than_the_reference_ops_in_torch_cuda_eager():
                    "paradis_model_b200_autograd_op_ms": t_ours, "ratio": t_ref / t_ours,
                    "peak_mem_GiB_both": mem}, fh)
     assert t_ours * 3 < t_ref
+
+
+@pytest.mark.parametrize("stride", [1, 2, 4])
+def test_physical_downsample_strided_kernel(stride):
+    """PhysicalDownsample (model/blocks.py:57-71) as one strided kernel: forward and input gradient against
+    GeoCyclic pad 2 + avg_pool2d on the same GPU; only the strided outputs are computed."""
+    import torch.nn.functional as F
+    from paradis_model_b200 import blocks
+    g = torch.Generator().manual_seed(stride)
+    x = torch.randn(2, 3, 33, 64, generator=g).cuda()
+    gy_shape = (2, 3, (33 - 1) // stride + 1, (64 - 1) // stride + 1)
+    gy = torch.randn(gy_shape, generator=g).cuda()
+    xr = x.clone().requires_grad_(True)
+    yr = F.avg_pool2d(O.geocyclic_pad(xr, 2), 5, stride, count_include_pad=False)
+    yr.backward(gy)
+    xc = x.clone().requires_grad_(True)
+    y = blocks.PhysicalDownsample(stride=stride).cuda()(xc)
+    y.backward(gy)
+    assert y.shape == yr.shape and relmax(y.detach().cpu(), yr.detach().cpu()) < 1e-6
+    assert relmax(xc.grad.cpu(), xr.grad.cpu()) < 1e-5
+
+
+def test_dwconv_rejects_meshes_where_both_caps_fold_onto_one_row():
+    with pytest.raises(RuntimeError, match="mesh too small"):
+        P().geocyclic_dwconv(torch.zeros(1, 2, 5, 16, device="cuda"), torch.zeros(2, 1, 5, 5, device="cuda"))
