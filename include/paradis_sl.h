@@ -166,6 +166,9 @@ int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* field, const
 #define PARADIS_BWD_ARRIVAL 1
 #define PARADIS_BWD_GATHER 2
 #define PARADIS_BWD_ALL 3
+/* OR-ed into PARADIS_BWD_ALL: use the warp-specialised row sweep (sl_rows.cuh) whenever its plan fits, also on meshes
+ * narrower than ~900 columns and for the 4x4 stencil, where the round-1 strip sweep is the default (tests). */
+#define PARADIS_BWD_ROWSWEEP 8
 size_t paradis_sl_advect_bwd_workspace(int B, int V, int arr_rows, int W);
 int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* grad_out,
                           const float* field, const float* u, const float* v, float* grad_field,

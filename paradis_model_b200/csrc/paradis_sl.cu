@@ -858,7 +858,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 template <bool EXACT, int INTERP>
-static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const BwdWs& L, char* ws) {
+static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const BwdWs& L, char* ws, bool forced) {
   constexpr int NT = Stencil<INTERP>::NT;
   const int H = P.H, W = P.W, planes = P.B * P.V;
   if (!(cfl_cells > 0.0f) || H < 8 || W < 32 || W > 32767) return false;
@@ -880,6 +880,9 @@ static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const
   S.nC = nC; S.nS = nS; S.wc = wc; S.nP = kRowsWarps - 1 - nC;
   if (S.nP < 1) return false;
   S.nsteps = (W + 32 * kStepSub - 1) / (32 * kStepSub);
+  // a row is cut into nsteps producer steps and at most kRowRecs rows are in flight: narrow meshes leave most of the
+  // producer warps without work (C2, 128x256: 1.27 ms/step against 0.75 for the strip sweep), so they keep the strip sweep
+  if (!forced && S.nsteps < 8) return false;
   S.total_rows = planes * P.ownN;
   S.pitch = (wc + NT - 1 + 3) & ~3;
   S.ring_stride = (S.ring + NT - 1) * S.pitch;
@@ -992,6 +995,8 @@ static int device_capacity(const void* kern, int threads, size_t smem, int& nsm)
 
 template <bool EXACT, int INTERP>
 static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_cells, const BwdWs& L, char* ws) {
+  const bool force_rows = (phases & PARADIS_BWD_ROWSWEEP) != 0;
+  phases &= PARADIS_BWD_ALL;
   const bool want_field = P.gfield != nullptr;
   const int planes = P.B * P.V;
   P.plane_filter = nullptr; P.plane_flag = nullptr; P.reach_limit = 1 << 20;
@@ -1003,7 +1008,8 @@ static int launch_bwd(Params P, int vec, cudaStream_t st, int phases, float cfl_
   if (bwd_mode == 2) return launch_general<EXACT, INTERP>(P, vec, st, want_field, phases, L.nblk);
   // (4x4 stencil: the round-1 strip sweep is still the faster kernel, 3.65 against 4.6 ms at C3; PARADIS_SL_BWD=3
   // forces the row sweep for it)
-  if ((bwd_mode == 3 || (bwd_mode == 0 && INTERP == 1)) && launch_rows<EXACT, INTERP>(P, st, cfl_cells, L, ws)) {
+  if ((bwd_mode == 3 || force_rows || (bwd_mode == 0 && INTERP == 1)) &&
+      launch_rows<EXACT, INTERP>(P, st, cfl_cells, L, ws, bwd_mode == 3 || force_rows)) {
     Params Q = P;
     Q.plane_filter = (unsigned char*)(ws + L.flag);
     Q.gu = nullptr; Q.gv = nullptr;                   // grad_u / grad_v are already complete
@@ -1073,7 +1079,8 @@ extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* g
   Params P;
   if (int rc = fill_params(P, geom, B, V, dt, interp, pole_fix)) return rc;
   if (!grad_out || !field || !u || !v) return fail(PARADIS_ERR_NULL_POINTER, "NULL tensor pointer");
-  if (phases < 1 || phases > 3) return fail(PARADIS_ERR_BAD_SHAPE, "phases must be 1, 2 or 3");
+  if ((phases & ~(PARADIS_BWD_ALL | PARADIS_BWD_ROWSWEEP)) || !(phases & PARADIS_BWD_ALL))
+    return fail(PARADIS_ERR_BAD_SHAPE, "phases must be 1, 2 or 3 (optionally | PARADIS_BWD_ROWSWEEP)");
   if ((grad_u == nullptr) != (grad_v == nullptr)) return fail(PARADIS_ERR_NULL_POINTER, "grad_u and grad_v must both be given or both be NULL");
   const BwdWs L = bwd_layout(B, V, P.arrN, P.W);
   if (!workspace || workspace_bytes < L.total)

@@ -258,8 +258,8 @@ def _sl_advect_backward(grad_out: Tensor, field: Tensor, u: Tensor, v: Tensor, t
     with torch.cuda.device(dev):
         rc = L.paradis_sl_advect_bwd(C.byref(g), _ptr(grad_out), _ptr(field), _ptr(u), _ptr(v), _ptr(gf), _ptr(gu),
                                      _ptr(gv), B, V, grad_out.stride(0), field.stride(0), u.stride(0), v.stride(0),
-                                     dt, interp, int(pole_fix), math, 3, cfl, _ptr(ws), ws_bytes,
-                                     _ptr(_status_word(dev)), _stream(field))
+                                     dt, interp, int(pole_fix), math, 3 | (8 if FORCE_ROW_SWEEP else 0), cfl, _ptr(ws),
+                                     ws_bytes, _ptr(_status_word(dev)), _stream(field))
     _lib.check(rc, "paradis_sl_advect_bwd")
     none = lambda: torch.empty(0, dtype=torch.float32, device=dev)
     return (gf if need_field else none(), gu if need_uv else none(), gv if need_uv else none())
@@ -301,6 +301,7 @@ _sl_advect.register_autograd(_sl_backward, setup_context=_sl_setup)
 
 
 DEFAULT_CFL_CELLS = 8.0
+FORCE_ROW_SWEEP = False     # tests: run the row-sweep backward also where the strip sweep is the default (PARADIS_BWD_ROWSWEEP)
 # read once at import (not inside traced code): PARADIS_SL_MATH=fast|exact overrides the math mode,
 # PARADIS_SL_CHECK=1 synchronises after every call and raises on a device-side contract violation
 _ENV_MATH = os.environ.get("PARADIS_SL_MATH", "")

@@ -13,6 +13,16 @@ pytestmark = pytest.mark.gpu
 DT = 21600 * 7.29212e-5 / 8
 
 
+@pytest.fixture(autouse=True, params=["default-backward", "row-sweep-forced"])
+def _backward_kernel(request):
+    """Every test runs twice: with the library's own choice of fused backward (row sweep on wide bilinear meshes, strip
+    sweep otherwise) and with the warp-specialised row sweep forced wherever its plan fits (PARADIS_BWD_ROWSWEEP)."""
+    from paradis_model_b200 import ops
+    ops.FORCE_ROW_SWEEP = request.param == "row-sweep-forced"
+    yield
+    ops.FORCE_ROW_SWEEP = False
+
+
 def P():
     import paradis_model_b200 as pkg
     return pkg
