@@ -325,6 +325,8 @@ def test_halo_violation_is_reported():
 
 
 def test_host_entry_matches_device_path():
+    from paradis_model_b200 import ops
+    ops.FORCE_ROW_SWEEP = False            # the host entry makes the library's own kernel choice: compare like with like
     H, W, B, V = 64, 128, 2, 5
     lat, lon, field, u, v, go = O.bench_inputs(H, W, B, V, False, DT)
     pkg = P()
