@@ -12,7 +12,8 @@ for (H, W, B, V, poles, cfl, interp) in [(96, 192, 1, 2, True, 3.0, "bilinear"),
     f, u, v, g = [t.cuda() for t in S.white_noise_inputs(H, W, B, V, cells_sigma=1.0, cells_clip=max(cfl / 1.5, 1.0))]
     R = RawAdvection(geo, B, V, interp, True, "fast", cfl)
     R.forward(f, u, v, S.DT_DEFAULT)
-    R.backward(g, f, u, v, S.DT_DEFAULT, 3)
+    R.backward(g, f, u, v, S.DT_DEFAULT, 3)          # the library's own choice of fused backward
+    R.backward(g, f, u, v, S.DT_DEFAULT, 3 | 8)      # the warp-specialised row sweep forced (TMA, mbarriers)
     torch.cuda.synchronize()
     P.check_status()
     x = torch.randn(1, 2, H, W, device="cuda", requires_grad=True)
@@ -27,3 +28,5 @@ for (H, W, C, k) in [(33, 70, 3, 3), (40, 64, 2, 5), (17, 24, 2, 7)]:
     P.geocyclic_dwconv(x, w, b).square().sum().backward()
     torch.cuda.synchronize()
     print("dwconv", H, W, k, "ok", float(x.grad.abs().sum()), float(w.grad.abs().sum()))
+    y = P.geocyclic_avgpool5(x, 2)
+    y.sum().backward()
