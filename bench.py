@@ -253,19 +253,19 @@ def run_b200(args):
         h_out = [torch.empty(Bg, V, H, W, pin_memory=True) for _ in range(4)]
         scratch = None
         n_e2e = max(2, min(args.steps, 5))
-        scratch = P.host_fwd_bwd(geo, *h_in, *h_out, dt, args.interp, True, args.math, 8, scratch, CFL_CELLS)
+        scratch = P.host_fwd_bwd(geo, *h_in, *h_out, dt, args.interp, True, args.math, 4, scratch, CFL_CELLS)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            scratch = P.host_fwd_bwd(geo, *h_in, *h_out, dt, args.interp, True, args.math, 8, scratch, CFL_CELLS)
+            scratch = P.host_fwd_bwd(geo, *h_in, *h_out, dt, args.interp, True, args.math, 4, scratch, CFL_CELLS)
         te = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         nbytes = 4 * pts_rank * 4
         e2e = {"value": world * pts_rank / float(te.item()), "unit": "grid-pt*ch/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes, "ms_per_step": float(te.item()) * 1e3, "steps": n_e2e,
-               "api": "paradis_sl_advect_fwd_bwd_host (pinned host tensors, 8-plane chunks, 3 streams)"}
+               "api": "paradis_sl_advect_fwd_bwd_host (pinned host tensors, 4-plane chunks, 4 streams)"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -128,12 +128,32 @@ __global__ void __launch_bounds__(256) sl_fwd_kernel(const Params P) {
 #pragma unroll
     for (int k = 0; k < VEC; ++k) { uu[k] = __ldcs(up + k); vv[k] = __ldcs(vp + k); ll[k] = __ldg(P.lon + x + k); }
   }
+#ifndef PSL_FWD_NO_PAIRS
+  if (!EXACT && VEC == 4) {
+    // FAST math: the 4 departure points of the thread as two packed pairs (FFMA2 / FMUL2 / FADD2), bit-identical to
+    // the scalar chain
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    Traj t;
-    trajectory<EXACT>(P, uu[k], vv[k], sp, cp, ll[k], t);
-    float dx, dy;
-    stencil_eval<INTERP, false, PEER>(P, f, pl, t, mean0, mean1, oo[k], dx, dy);
+    for (int h = 0; h < 2; ++h) {
+      Traj2 t2;
+      trajectory_2(P, make_float2(uu[2 * h], uu[2 * h + 1]), make_float2(vv[2 * h], vv[2 * h + 1]), f2s(sp), f2s(cp),
+                   make_float2(ll[2 * h], ll[2 * h + 1]), t2);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const Traj t = traj_half(t2, e);
+        float dx, dy;
+        stencil_eval<INTERP, false, PEER>(P, f, pl, t, mean0, mean1, oo[2 * h + e], dx, dy);
+      }
+    }
+  } else
+#endif
+  {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      Traj t;
+      trajectory<EXACT>(P, uu[k], vv[k], sp, cp, ll[k], t);
+      float dx, dy;
+      stencil_eval<INTERP, false, PEER>(P, f, pl, t, mean0, mean1, oo[k], dx, dy);
+    }
   }
   float* op = P.out + ((long long)pl * P.ownN + r) * P.W + x;
   if (VEC == 4) __stcs(reinterpret_cast<float4*>(op), *reinterpret_cast<float4*>(oo));
@@ -1182,7 +1202,13 @@ extern "C" int paradis_geocyclic_pad_bwd(const float* gy, float* gx, int64_t pla
 // host-buffer entry: chunks of planes pipelined over three streams (H2D | kernels | D2H overlap
 // across chunks because consecutive chunks live on different streams and slots)
 // ---------------------------------------------------------------------------------------------
-static constexpr int kSlots = 3;
+// chunks in flight (each on its own stream): H2D of one, kernels of another, D2H of a third overlap; more slots keep
+// both copy engines busy across the slot-reuse dependency.  PARADIS_SL_HOST_SLOTS overrides (2..8).
+static constexpr int kMaxSlots = 8;
+static int host_slots() {
+  static const int n = [] { const char* v = getenv("PARADIS_SL_HOST_SLOTS"); int k = v ? atoi(v) : 4;   /* 25.4-26.5 ms at C3 for 3-6 slots: PCIe bound */ return k < 2 ? 2 : (k > kMaxSlots ? kMaxSlots : k); }();
+  return n;
+}
 
 struct HostSlot { size_t field, u, v, gout, out, gfield, gu, gv, wsf, wsb, status, total; };
 static HostSlot host_slot_layout(int H, int W, int c) {
@@ -1200,7 +1226,7 @@ static HostSlot host_slot_layout(int H, int W, int c) {
 
 extern "C" size_t paradis_sl_host_scratch_bytes(int H, int W, int chunk_planes) {
   if (H <= 0 || W <= 0 || chunk_planes <= 0) return 0;
-  return host_slot_layout(H, W, chunk_planes).total * kSlots;
+  return host_slot_layout(H, W, chunk_planes).total * host_slots();
 }
 
 extern "C" int paradis_sl_advect_fwd_bwd_host(const paradis_sl_geom* geom, const float* h_field, const float* h_u,
@@ -1217,9 +1243,10 @@ extern "C" int paradis_sl_advect_fwd_bwd_host(const paradis_sl_geom* geom, const
   if (geom->own_row0 != 0 || geom->own_rows != H || geom->arr_rows != H || geom->fld_rows != H)
     return fail(PARADIS_ERR_BAD_SHAPE, "host entry works on the full mesh");
   const HostSlot L = host_slot_layout(H, W, chunk_planes);
+  const int kSlots = host_slots();
   if (!d_scratch || scratch_bytes < L.total * kSlots)
     return fail(PARADIS_ERR_WORKSPACE, "host-entry scratch too small (%zu < %zu bytes)", scratch_bytes, L.total * kSlots);
-  cudaStream_t st[kSlots];
+  cudaStream_t st[kMaxSlots];
   for (int i = 0; i < kSlots; ++i)
     if (cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess)
       return fail(PARADIS_ERR_CUDA, "cudaStreamCreate failed");
