@@ -81,6 +81,39 @@ def ncu_traffic(phase, captured_config):
         return None
 
 
+def aux_kernel_rooflines(torch, P, H, W, dev, peak):
+    C = 64
+    x = torch.randn(1, C, H, W, device=dev)
+    w5 = torch.randn(C, 1, 5, 5, device=dev) / 5
+    pad2 = torch.empty(1, C, H + 4, W + 4, device=dev)
+
+    def timed(fn, n=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    el, elp = x.numel(), pad2.numel()
+    cases = {
+        "geocyclic_pad_fwd p=2": (lambda: P.geocyclic_pad(x, 2), 4 * (el + elp)),
+        "geocyclic_pad_bwd p=2": (lambda: torch.ops.paradis.geocyclic_pad_backward(pad2, 2), 4 * (el + elp)),
+        "geocyclic_dwconv_fwd k=5": (lambda: P.geocyclic_dwconv(x, w5), 8 * el),
+        "geocyclic_avgpool5 stride 4": (lambda: P.geocyclic_avgpool5(x, 4), 4 * el + 4 * el // 16),
+    }
+    out = {}
+    for name, (fn, nbytes) in cases.items():
+        ms = timed(fn)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "achieved": gbs, "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes": nbytes}
+    return out
+
+
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons during the timed region (NVML, 20 ms period)."""
 
@@ -306,6 +339,10 @@ def run_b200(args):
             "clocks": clocks, "gpu_launches": (12 if bilinear else 15) * args.steps, "wall_ms_timed_region": wall_ms}
     if e2e:
         line["e2e"] = e2e
+    if world == 1:
+        # the other kernels of the boundary (GeoCyclic padding op, padding fused into the depthwise convolution, strided
+        # PhysicalDownsample), one [1, 64, H, W] tensor each: GB/s of algorithmic traffic against the same measured peak
+        line["aux_kernels"] = aux_kernel_rooflines(torch, P, H, W, dev, peak)
     if world == 1 and not args.no_cpu:
         sec, cores = cpu_port_time(H, W, poles, args.interp, CPU_SAMPLE_V, 2)
         line["cpu_baseline"] = {"value": CPU_SAMPLE_V * H * W / sec, "unit": "grid-pt*ch/s", "cores": cores,

@@ -445,7 +445,9 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
         mean0 = __ldg(P.fmean + 2 * pl); mean1 = __ldg(P.fmean + 2 * pl + 1);
         gm0 = __ldg(P.gmean + 2 * pl); gm1 = __ldg(P.gmean + 2 * pl + 1);
       }
-      for (int y = max(sg.y_first, arr_lo); y <= min(sg.y_last, arr_hi - 1); ++y, ++n) {
+      const int y_begin = max(sg.y_first, arr_lo);
+      int hbase = (y_begin - sg.y_first) % ring;      // ring slot of the row that retires after the arrival row
+      for (int y = y_begin; y <= min(sg.y_last, arr_hi - 1); ++y, ++n, hbase = hbase + 1 == ring ? 0 : hbase + 1) {
         const int row_end = (n + 1) * S.nsteps;
         const int st = n % kRowStages, rs = n % kRowRecs;
         // Every producer warp takes part in every row of both pipelines (it arrives on stage_free and rec_full
@@ -462,7 +464,6 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
         const float sp = __ldg(P.sin_lat + y), cp = __ldg(P.cos_lat + y);
         const int hx = __ldg(S.hx_tab + y);
         const bool core = (y >= sg.ra) && (y < sg.rb) && gu_pl != nullptr;
-        const int hbase = (y - sg.y_first) % ring;     // ring slot of the row that retires after this arrival row
         const bool pole_row = P.pole_fix && (y == 0 || y == P.H - 1);
         const float gpole = y == 0 ? gm0 : gm1;
         for (; next < row_end; next += S.nP) {
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
             for (int q = 0; q < kStreams; ++q) {
               idx[q] = idx[q] + 1 == W ? 0 : idx[q] + 1;
               inn[q] = (s + 1 < k) && (lane * k + s + 1 < len) && T[q].wc > 0;
-              nxt[q] = inn[q] ? recs[idx[q]] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+              nxt[q] = recs[idx[q]];                       // always a valid address; `inn` masks the key when it is used
             }
 #ifndef PSL_DBG_NOCONSUME
             if (fold_row) {
