@@ -891,7 +891,7 @@ static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const
   S.planes = planes; S.rr = rr; S.ring = 2 * rr + NT;
   static const int env_nc = env_int("PARADIS_SL_ROWS_NC", 0);
   int nC = env_nc > 0 ? env_nc : (INTERP == 1 ? 5 : 8);
-  if (nC > kRowsWarps - 2) nC = kRowsWarps - 2;
+  if (nC > kRowsMaxConsumers) nC = kRowsMaxConsumers;
   int nS = nC * kStreams;                                  // strips: kStreams per consumer warp
   int wc = ((W + nS - 1) / nS + 3) & ~3;
   if (wc < 32) wc = 32;

@@ -57,10 +57,14 @@ constexpr int kTagBytes = 512;     // clash tags per strip (hashed, power of two
 #endif
 constexpr int kStreams = PSL_ROWS_STREAMS;   // strips a consumer warp works on in an interleaved manner
 constexpr int kRowsMaxCtas = 192;
+// Warp budget: loader + producers + consumers.  20 warps = 640 threads -> 96 registers, no spills.  (Re-partitioning
+// the register file between the roles with setmaxnreg -- 16 producers at 96-104 registers, loader + 7 consumers at
+// 40-64 -- was tried: slower, 2.2-2.9 ms against 1.82, and two of the four splits hung; removed.)
 #ifndef PSL_ROWS_WARPS
-#define PSL_ROWS_WARPS 20          // loader + producers + consumers; 20 warps = 640 threads -> 96 registers, no spills
+#define PSL_ROWS_WARPS 20
 #endif
 constexpr int kRowsWarps = PSL_ROWS_WARPS;
+constexpr int kRowsMaxConsumers = kRowsWarps - 2;
 
 struct RowsPlan {
   int planes, rr, ring;            // ring = 2 rr + NT destination rows
@@ -403,7 +407,13 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
   const int arr_lo = P.arr0, arr_hi = P.arr0 + P.arrN;
   RowsSeg sg;
 
-  if (warp == 0) {
+  // role of this warp: 0 = loader, then nP producers, then nC consumers
+  const bool is_loader = warp == 0;
+  const int prod0 = 1;
+  const bool is_producer = warp >= prod0 && warp < prod0 + S.nP;
+  const int cons0 = 1 + S.nP;
+
+  if (is_loader) {
     // ===================================== loader =====================================
     // (an L2 prefetch of the `field` row entering the stencil window, issued from this warp's idle lanes, was
     // measured: no effect, 1.837 against 1.835 ms)
@@ -427,9 +437,9 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
     return;
   }
 
-  if (warp <= S.nP) {
+  if (is_producer) {
     // ==================================== producers ====================================
-    const int p = warp - 1;
+    const int p = warp - prod0;
     int n = 0;
     int next = p;                     // global step index (row sequence number * nsteps + step) this warp does next
     bool violated = false;
@@ -543,9 +553,9 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
     return;
   }
 
-  if (warp <= S.nP + S.nC) {
+  if (warp >= cons0 && warp < cons0 + S.nC) {
     // ==================================== consumers ====================================
-    const int cidx = warp - 1 - S.nP;
+    const int cidx = warp - cons0;
     const int pitch = S.pitch;
     RowsStrip T[kStreams];
     int sidx[kStreams];
