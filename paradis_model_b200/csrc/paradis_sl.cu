@@ -73,32 +73,54 @@ __device__ __forceinline__ float warp_row_sum(const float* row, int W, int lane)
   return s;
 }
 
-// means[pl][k], k = 0: global row 0, k = 1: global row H-1 of tensor `t` whose window is (row0, rows)
-__global__ void pole_means_kernel(const float* __restrict__ t, long long sB, int V, int rows, int row0,
-                                  int H, int W, int planes, float* __restrict__ means) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= planes * 2) return;
-  const int pl = warp >> 1, k = warp & 1;
+// deterministic zonal sum of one row by one 128-thread CTA: fixed per-thread order, shuffle tree, the four warp
+// partials added in warp order (one warp walking a 1440-element row took 8.5 us per launch, five launches per step)
+constexpr int kPoleThreads = 128;
+__device__ __forceinline__ float block_row_sum(const float* row, int W) {
+  __shared__ float part[kPoleThreads / 32];
+  float s = 0.0f;
+  for (int x = threadIdx.x; x < W; x += kPoleThreads) s += row[x];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float t = part[0];
+#pragma unroll
+  for (int w = 1; w < kPoleThreads / 32; ++w) t += part[w];
+  __syncthreads();
+  return t;
+}
+
+// means[pl][k], k = 0: global row 0, k = 1: global row H-1 of tensor `t` whose window is (row0, rows); one CTA per
+// (plane, pole).  A second tensor (t2 -> means2, its own window) rides in the same launch (backward: field, grad_out).
+__global__ void __launch_bounds__(kPoleThreads) pole_means_kernel(const float* __restrict__ t, long long sB, int V, int rows, int row0,
+                                                                  int H, int W, int planes, float* __restrict__ means,
+                                                                  const float* __restrict__ t2, long long sB2, int rows2,
+                                                                  int row02, float* __restrict__ means2) {
+  int job = blockIdx.x;
+  if (job >= planes * 2) {
+    if (!t2) return;
+    job -= planes * 2; t = t2; sB = sB2; rows = rows2; row0 = row02; means = means2;
+  }
+  const int pl = job >> 1, k = job & 1;
   const int gr = k ? H - 1 : 0, lr = gr - row0;
   float m = 0.0f;
   if (lr >= 0 && lr < rows) {
     const float* row = plane_ptr(t, sB, V, rows, W, pl) + (long long)lr * W;
-    m = warp_row_sum(row, W, lane) / (float)W;
+    m = block_row_sum(row, W) / (float)W;
   }
-  if (lane == 0) means[warp] = m;
+  if (threadIdx.x == 0) means[job] = m;
 }
 
-// out rows 0 / H-1 <- their zonal mean (second enforce_pole_continuity, advection.py:169)
-__global__ void pole_rows_fix_kernel(float* __restrict__ t, int rows, int row0, int H, int W, int planes) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= planes * 2) return;
-  const int pl = warp >> 1, k = warp & 1;
+// out rows 0 / H-1 <- their zonal mean (second enforce_pole_continuity, advection.py:169); one CTA per (plane, pole)
+__global__ void __launch_bounds__(kPoleThreads) pole_rows_fix_kernel(float* __restrict__ t, int rows, int row0, int H, int W, int planes) {
+  const int job = blockIdx.x;
+  const int pl = job >> 1, k = job & 1;
   const int gr = k ? H - 1 : 0, lr = gr - row0;
   if (lr < 0 || lr >= rows) return;
   float* row = t + ((long long)pl * rows + lr) * W;
-  const float m = warp_row_sum(row, W, lane) / (float)W;
-  __syncwarp();
-  for (int x = lane; x < W; x += 32) row[x] = m;
+  const float m = block_row_sum(row, W) / (float)W;
+  for (int x = threadIdx.x; x < W; x += kPoleThreads) row[x] = m;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -687,8 +709,8 @@ extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* f
       return fail(PARADIS_ERR_WORKSPACE, "forward workspace too small (%zu bytes)", workspace_bytes);
     float* fmean = (float*)workspace;
     P.fmean = fmean;
-    const int warps = planes * 2;
-    pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(field, field_sB, V, P.fldN, P.fld0, P.H, P.W, planes, fmean);
+    pole_means_kernel<<<planes * 2, kPoleThreads, 0, st>>>(field, field_sB, V, P.fldN, P.fld0, P.H, P.W, planes, fmean, nullptr, 0,
+                                                            0, 0, nullptr);
   }
   const bool vec_ok = (P.W % 4 == 0) && aligned16(field) && aligned16(u) && aligned16(v) && aligned16(out) &&
                       aligned16(P.lon) && (u_sB % 4 == 0) && (v_sB % 4 == 0);
@@ -707,10 +729,7 @@ extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* f
     else sl_fwd_pair_kernel<1, false><<<pgrid, 256, 0, st>>>(P, gpr);
   } else if (interp == 1) { if (exact) launch_fwd<true, 1>(P, vec, grid, st); else launch_fwd<false, 1>(P, vec, grid, st); }
   else             { if (exact) launch_fwd<true, 2>(P, vec, grid, st); else launch_fwd<false, 2>(P, vec, grid, st); }
-  if (pole_fix) {
-    const int warps = planes * 2;
-    pole_rows_fix_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(out, P.ownN, P.own0, P.H, P.W, planes);
-  }
+  if (pole_fix) pole_rows_fix_kernel<<<planes * 2, kPoleThreads, 0, st>>>(out, P.ownN, P.own0, P.H, P.W, planes);
   return check_launch("paradis_sl_advect_fwd");
 }
 
@@ -976,8 +995,7 @@ static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const
   }
   if (P.pole_fix) {
     // adjoint of the first enforce_pole_continuity (advection.py:129): pole rows of grad_field get their zonal mean
-    const int warps = planes * 2;
-    pole_rows_fix_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(P.gfield, P.ownN, P.own0, H, W, planes);
+    pole_rows_fix_kernel<<<planes * 2, kPoleThreads, 0, st>>>(P.gfield, P.ownN, P.own0, H, W, planes);
   }
   return true;
 }
@@ -1119,11 +1137,9 @@ extern "C" int paradis_sl_advect_bwd(const paradis_sl_geom* geom, const float* g
   P.blkmax = grad_field ? (unsigned char*)(ws + L.blkmax) : nullptr;
   P.cls = grad_field ? (signed char*)(ws + L.cls) : nullptr;
   P.nblk = L.nblk;
-  if (pole_fix && (phases & PARADIS_BWD_ARRIVAL)) {
-    const int warps = planes * 2;
-    pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(field, field_sB, V, P.fldN, P.fld0, P.H, P.W, planes, fmean);
-    pole_means_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(grad_out, gout_sB, V, P.uvgN, P.uvg0, P.H, P.W, planes, gmean);
-  }
+  if (pole_fix && (phases & PARADIS_BWD_ARRIVAL))      // zonal pole means of field and grad_out in one launch
+    pole_means_kernel<<<planes * 4, kPoleThreads, 0, st>>>(field, field_sB, V, P.fldN, P.fld0, P.H, P.W, planes, fmean, grad_out,
+                                                            gout_sB, P.uvgN, P.uvg0, gmean);
   const bool vec_ok = (P.W % 4 == 0) && aligned16(field) && aligned16(u) && aligned16(v) && aligned16(grad_out) &&
                       aligned16(P.lon) && (!grad_u || (aligned16(grad_u) && aligned16(grad_v))) &&
                       (!grad_field || aligned16(grad_field)) &&   // the sweep retires rows with float4 stores
