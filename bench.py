@@ -51,6 +51,9 @@ def parse():
                     help="N>1: latitude bands of ONE global problem (strong scaling; default for c3) or one replica "
                          "per GPU (weak scaling)")
     ap.add_argument("--no-batch", action="store_true", help="latband: skip the batch-sharded comparison leg")
+    ap.add_argument("--pull-field", action="store_true",
+                    help="latband: pull the neighbours' field rows into a local buffer after the publish barrier instead of "
+                         "reading them in place with the stencil taps (measured: no gain)")
     ap.add_argument("--no-p2p", action="store_true", help="latband: NCCL transport for the field halo too")
     ap.add_argument("--no-graph", action="store_true", help="latband: eager autograd step instead of a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")

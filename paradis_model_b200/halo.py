@@ -176,32 +176,57 @@ class PeerHalo:
     two small copies, barrier (everybody's rows are in place).  The kernels then dereference
     `lo_ptr` / `hi_ptr` -- addresses inside the NEIGHBOURS' outboxes -- directly."""
 
-    def __init__(self, plan: BandPlan, B: int, V: int, device, group=None):
+    def __init__(self, plan: BandPlan, B: int, V: int, device, group=None, pull_field: bool = False):
         import torch.distributed._symmetric_memory as symm
         self.plan, self.planes = plan, B * V
         h, W = plan.halo, plan.W
         # slot 0: field; slots 1..3: u, v, grad_out of the backward.  [slot][side][plane][h][W]
         self.box = symm.empty((4, 2, B * V, h, W), dtype=torch.float32, device=device)
         self.hdl = symm.rendezvous(self.box, group=group if group is not None else dist.group.WORLD)
-        side_bytes = B * V * h * W * 4
+        side_elems = B * V * h * W
+        side_bytes = side_elems * 4
         ptrs = self.hdl.buffer_ptrs
         south = int(ptrs[plan.rank - 1]) if plan.rank > 0 else 0
         north = int(ptrs[plan.rank + 1]) if plan.rank < plan.world - 1 else 0
         # my southern halo = the southern neighbour's LAST rows (its side 1); northern halo = side 0 of the northern one
         self.lo = [south + (2 * k + 1) * side_bytes if south else 0 for k in range(4)]
         self.hi = [north + (2 * k) * side_bytes if north else 0 for k in range(4)]
-        self.lo_ptr, self.hi_ptr = self.lo[0], self.hi[0]
+        # pull_field=True: the `field` halo rows are PULLED into local memory right after the publish barrier (one
+        # peer-memory copy per side over NVLink, no NCCL) instead of being read in place by the stencil taps.  Measured
+        # at N=2: forward 0.238 -> 0.227 ms, backward unchanged, step 1.381 -> 1.407 ms (the copies cost more than the
+        # remote taps): off by default.  The u / v / grad_out halo rows of the backward are streamed in place by the
+        # row-sweep kernel's TMA bulk copies either way.
+        self.local = None
+        self._peer_views = (None, None)
+        if pull_field:
+            self.local = torch.empty((2, B * V, h, W), dtype=torch.float32, device=device)
+            shape = (B * V, h, W)
+            lo_view = self.hdl.get_buffer(plan.rank - 1, shape, torch.float32, 1 * side_elems) if south else None
+            hi_view = self.hdl.get_buffer(plan.rank + 1, shape, torch.float32, 0) if north else None
+            self._peer_views = (lo_view, hi_view)
+            self.lo_ptr = self.local[0].data_ptr() if south else 0
+            self.hi_ptr = self.local[1].data_ptr() if north else 0
+        else:
+            self.lo_ptr, self.hi_ptr = self.lo[0], self.hi[0]
 
     def _put(self, slot: int, t: torch.Tensor) -> None:
         h, W, n = self.plan.halo, self.plan.W, self.plan.rows
         self.box[slot, 0].copy_(t[:, :, :h].reshape(self.planes, h, W))
         self.box[slot, 1].copy_(t[:, :, n - h:].reshape(self.planes, h, W))
 
+    def _pull_field(self) -> None:
+        if self.local is None:
+            return
+        for k, view in enumerate(self._peer_views):
+            if view is not None:
+                self.local[k].copy_(view)
+
     def publish(self, field: torch.Tensor) -> None:
         assert field.shape[2] == self.plan.rows and field.shape[0] * field.shape[1] == self.planes
         self.hdl.barrier(channel=0)
         self._put(0, field)
         self.hdl.barrier(channel=0)
+        self._pull_field()
 
     def publish_backward(self, field: torch.Tensor, u: torch.Tensor, v: torch.Tensor, g: torch.Tensor) -> None:
         """One barrier pair for all four tensors of the backward."""
@@ -209,6 +234,7 @@ class PeerHalo:
         for slot, t in enumerate((field, u, v, g)):
             self._put(slot, t)
         self.hdl.barrier(channel=0)
+        self._pull_field()
 
     def peer(self):
         return (self.lo_ptr, self.hi_ptr, self.plan.halo)
@@ -293,8 +319,11 @@ def bench_latband(args, workload, rank, world, dev):
     peer, transport = None, "NCCL send/recv for field, grad_out, u, v"
     if not getattr(args, "no_p2p", False):
         try:
-            peer = PeerHalo(plan, Bg, V, dev)
-            transport = "all halos (field, grad_out, u, v) read in place over NVLink peer memory (symmetric memory), no NCCL on the data path"
+            peer = PeerHalo(plan, Bg, V, dev, pull_field=getattr(args, "pull_field", False))
+            transport = ("halos over NVLink peer memory (symmetric memory), no NCCL on the data path: u, v, grad_out rows streamed in "
+                         "place by TMA bulk copies inside the backward kernel, field rows "
+                         + ("pulled into a local buffer by one peer copy per side after the publish barrier"
+                            if getattr(args, "pull_field", False) else "read in place by the stencil taps"))
         except Exception as exc:   # symmetric memory unavailable: NCCL transport for everything
             transport += f" (symmetric memory unavailable: {type(exc).__name__})"
 
