@@ -82,6 +82,14 @@ def lib():
                 f"{path} is missing: build it with `python -m paradis_model_b200.build` "
                 "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this operator."
                 + (f"\nThe automatic build failed: {build_error}" if build_error is not None else ""))
+        if path == LIB_PATH:
+            try:                              # never rebuilt behind the caller's back, but never silently stale either
+                from .build import is_stale
+                if is_stale():
+                    import warnings
+                    warnings.warn(f"{path} is older than its CUDA sources: rebuild with `python -m paradis_model_b200.build`")
+            except Exception:
+                pass
         handle = C.CDLL(path)
         for name, (res, args) in _PROTOS.items():
             fn = getattr(handle, name)
