@@ -956,10 +956,14 @@ static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const
   {
     // Cost-balanced partition.  A row costs the consumers k(y) = steps of 32 records they scan for it (the whole
     // circle near the poles) plus a constant for the producers' share; CTA boundaries are placed at equal cumulative
-    // cost and snapped onto a plane boundary when they fall within min_seg rows of one (a segment costs ring - 1
-    // extra arrival rows).  Only balance depends on this model, results do not.
+    // cost and snapped onto a plane boundary when they fall within min_seg rows of one.  Only balance depends on
+    // this model, results do not.
     static const int env_w0 = env_int("PARADIS_SL_ROWS_W0", 6);
-    const int ownN = P.ownN, min_seg = 2 * S.ring;
+    static const int env_minseg = env_int("PARADIS_SL_ROWS_MINSEG", -1);
+    // snapping threshold: a boundary this close to a plane boundary moves onto it.  It trades the ring warm-up of a tiny
+    // segment (ring - 1 extra arrival rows) against rows of imbalance; 2 * ring cost 5 % at C3 and 11-22 % on thin
+    // latitude bands (1.82 -> 1.72 ms; a 62-row polar band 0.54 -> 0.42 ms), 3/4 ring is the measured optimum
+    const int ownN = P.ownN, min_seg = env_minseg >= 0 ? env_minseg : (3 * S.ring) / 4;
     std::vector<double> pre(ownN + 1, 0.0);
     for (int r = 0; r < ownN; ++r) {
       const double lat = (double)P.min_lat + (P.own0 + r) * dphi;

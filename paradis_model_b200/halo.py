@@ -85,11 +85,14 @@ def band_rows(H: int, world: int, cost: Optional[List[float]] = None) -> List[Tu
     return out
 
 
-def row_costs(H: int, W: int, cfl_cells: float, strip: int = 288, base: float = 6.0) -> List[float]:
+def row_costs(H: int, W: int, cfl_cells: float, strip: int = 288, base: float = None) -> List[float]:
     """Relative backward cost of a row on a pole-to-pole mesh, the model the row-sweep kernel balances its own CTAs
     with (csrc/paradis_sl.cu, launch_rows): a constant for the producers plus the number of 32-record steps a
     consumer scans for the row -- its strip plus the longitudinal reach of the row either side, which grows as
     1 / cos(lat) and becomes the whole circle next to the poles."""
+    import os
+    if base is None:      # measured on single bands (tools/band_local.py): the bands balance best without a constant term
+        base = float(os.environ.get("PARADIS_SL_BAND_BASE", "0"))
     dphi = math.pi / max(H - 1, 1)
     delta = cfl_cells * dphi
     out = []
