@@ -128,6 +128,14 @@ int paradis_geocyclic_dwconv_bwd_weight(const float* x, const float* gy, float* 
  * computes the strided outputs.  x [B, C, H, W] -> y [B, C, (H - 1) / stride + 1, (W - 1) / stride + 1]. */
 int paradis_geocyclic_avgpool5_fwd(const float* x, float* y, int B, int C, int H, int W, int stride, void* stream);
 
+/* ---- Latitude-band halo outbox (no counterpart in the reference, whose only parallelism is DDP, train.py:49) ----
+ * Copies the first and the last `h` rows of `n` (1..4) band tensors [B, V, rows, W] (batch stride src_sB[k] elements,
+ * inner three dims contiguous) into box[n][2][B*V][h][W] -- side 0 = first rows, side 1 = last rows -- in ONE launch.
+ * `box` is the symmetric-memory buffer the latitude neighbours read their halo rows from over NVLink
+ * (paradis_sl_geom.fld_peer_* / arr_peer_*).  src and src_sB are HOST arrays, read before the call returns. */
+int paradis_halo_pack(const float* const* src, const int64_t* src_sB, int n, int B, int V, int rows, int W, int h,
+                      float* box, void* stream);
+
 /* ---- Semi-Lagrangian advection core: model/advection.py:129-169 --------------------
  * (pole mean -> rotated-pole backtrack -> pixel coords -> GeoCyclic pad -> grid_sample
  *  -> pole mean), fused.

@@ -46,6 +46,7 @@ _PROTOS = {
     "paradis_geocyclic_dwconv_bwd_weight": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                       _P, C.c_size_t, _P]),
     "paradis_geocyclic_avgpool5_fwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "paradis_halo_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "paradis_sl_advect_fwd_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "paradis_sl_advect_fwd": (C.c_int, [C.POINTER(Geom), _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_float, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P]),

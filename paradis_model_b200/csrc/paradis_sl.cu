@@ -896,6 +896,102 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// Min-max partition of the concatenated (plane, own row) space into `grid` contiguous CTA ranges.
+// Cost of a range = sum over its segments (one per plane it touches) of the cost of the ARRIVAL rows the segment sweeps:
+// its own rows plus the ring - 1 warm-up rows, clipped to the arrival window.  A row costs w0 + k(y), k = 32-record
+// steps a consumer scans for it (the whole circle near the poles).  The smallest per-CTA budget T for which a greedy
+// left-to-right fill needs at most `grid` ranges is found by bisection; tiny segments are avoided by construction
+// (they pay a full warm-up).  An earlier version split proportionally to the own rows' cost and snapped boundaries
+// onto plane boundaries: 5 % slower at C3, 11-22 % on thin latitude bands.  Only balance depends on the model.
+// The result is cached per shape (it costs ~1 ms of host time).
+struct RowsPartKey { long long v[14]; };
+struct RowsPartEntry { RowsPartKey key; int bound[kRowsMaxCtas + 1]; bool valid; };
+
+template <int INTERP>
+static void rows_partition(const Params& P, RowsPlan& S, const ReachModel& reach, int wc, int planes, int grid) {
+  constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
+  static const int env_w0 = env_int("PARADIS_SL_ROWS_W0", 6);
+  static const int env_wcore = env_int("PARADIS_SL_ROWS_WCORE", 0);   // extra cost of a row whose grad_u / grad_v the segment writes
+  static thread_local RowsPartEntry cache[8];
+  static thread_local int cache_next = 0;
+  RowsPartKey key;
+  memset(&key, 0, sizeof(key));
+  const int H = P.H, W = P.W, ownN = P.ownN;
+  int fbits[2];
+  memcpy(&fbits[0], &P.min_lat, 4); memcpy(&fbits[1], &P.d_lat, 4);
+  const long long kv[14] = {H, W, planes, P.own0, ownN, P.arr0, P.arrN, S.rr, NT, wc, grid, env_w0, fbits[0], fbits[1]};
+  memcpy(key.v, kv, sizeof(kv));
+  for (auto& e : cache)
+    if (e.valid && memcmp(&e.key, &key, sizeof(key)) == 0) { memcpy(S.bound, e.bound, sizeof(S.bound)); return; }
+
+  const double dphi = (double)P.d_lat / (H - 1);
+  std::vector<double> A(H + 1, 0.0);                       // prefix of the arrival-row costs over global rows
+  for (int y = 0; y < H; ++y) {
+    const double lat = (double)P.min_lat + y * dphi;
+    const int hx = halo_cells(reach, (float)sin(lat), (float)cos(lat));
+    int len = wc + 2 * (hx < W ? hx : W);
+    if (len > W) len = W;
+    int k = (len + 31) >> 5;
+    if ((k & 3) == 0) ++k;
+    A[y + 1] = A[y] + env_w0 + k;
+  }
+  const int arr_lo = P.arr0, arr_hi = P.arr0 + P.arrN;
+  auto seg_cost = [&](int ra, int rb) {                     // destination rows [ra, rb) (global) of one plane
+    int y0 = ra - (S.ring - 1) + S.rr - OMIN, y1 = rb - 1 + S.rr - OMIN;
+    if (y0 < arr_lo) y0 = arr_lo;
+    if (y1 > arr_hi - 1) y1 = arr_hi - 1;
+    return (y1 >= y0 ? A[y1 + 1] - A[y0] : 0.0) + (double)env_wcore * (rb - ra);
+  };
+  const long long total = (long long)planes * ownN;
+  const double plane_cost = seg_cost(P.own0, P.own0 + ownN);
+  // greedy fill with budget T starting at position b: returns the end of the range (> b unless one row exceeds T)
+  auto fill = [&](long long b, double T) {
+    double used = 0.0;
+    long long e = b;
+    while (e < total) {
+      const int r = (int)(e % ownN);
+      if (r == 0 && used + plane_cost <= T) { used += plane_cost; e += ownN; continue; }   // a whole plane fits
+      // largest rb in (r, ownN] with used + seg_cost(own0 + r, own0 + rb) <= T (seg_cost is monotone in rb)
+      int lo = r, hi = ownN;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (used + seg_cost(P.own0 + r, P.own0 + mid) <= T) lo = mid; else hi = mid - 1;
+      }
+      if (lo == r) break;
+      used += seg_cost(P.own0 + r, P.own0 + lo);
+      e += lo - r;
+      if (lo < ownN) break;
+    }
+    return e;
+  };
+  auto ranges_needed = [&](double T) {
+    long long b = 0;
+    int n = 0;
+    while (b < total) {
+      const long long e = fill(b, T);
+      if (e == b) return 1 << 30;
+      b = e; ++n;
+      if (n > grid) break;
+    }
+    return n;
+  };
+  double lo = 0.0, hi = plane_cost * planes + 1.0;
+  for (int it = 0; it < 40; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (ranges_needed(mid) <= grid) hi = mid; else lo = mid;
+  }
+  long long b = 0;
+  S.bound[0] = 0;
+  for (int c = 1; c <= grid; ++c) {
+    if (b < total) b = fill(b, hi);
+    S.bound[c] = (int)b;
+  }
+  S.bound[grid] = (int)total;
+  RowsPartEntry& e = cache[cache_next];
+  cache_next = (cache_next + 1) % 8;
+  e.key = key; memcpy(e.bound, S.bound, sizeof(S.bound)); e.valid = true;
+}
+
 template <bool EXACT, int INTERP>
 static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const BwdWs& L, char* ws, bool forced) {
   constexpr int NT = Stencil<INTERP>::NT;
@@ -953,45 +1049,7 @@ static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const
   if (grid < 1) grid = 1;
   if (grid > nsm) grid = nsm;
   if (grid > kRowsMaxCtas) grid = kRowsMaxCtas;
-  {
-    // Cost-balanced partition.  A row costs the consumers k(y) = steps of 32 records they scan for it (the whole
-    // circle near the poles) plus a constant for the producers' share; CTA boundaries are placed at equal cumulative
-    // cost and snapped onto a plane boundary when they fall within min_seg rows of one.  Only balance depends on
-    // this model, results do not.
-    static const int env_w0 = env_int("PARADIS_SL_ROWS_W0", 6);
-    static const int env_minseg = env_int("PARADIS_SL_ROWS_MINSEG", -1);
-    // snapping threshold: a boundary this close to a plane boundary moves onto it.  It trades the ring warm-up of a tiny
-    // segment (ring - 1 extra arrival rows) against rows of imbalance; 2 * ring cost 5 % at C3 and 11-22 % on thin
-    // latitude bands (1.82 -> 1.72 ms; a 62-row polar band 0.54 -> 0.42 ms), 3/4 ring is the measured optimum
-    const int ownN = P.ownN, min_seg = env_minseg >= 0 ? env_minseg : (3 * S.ring) / 4;
-    std::vector<double> pre(ownN + 1, 0.0);
-    for (int r = 0; r < ownN; ++r) {
-      const double lat = (double)P.min_lat + (P.own0 + r) * dphi;
-      const int hx = halo_cells(reach, (float)sin(lat), (float)cos(lat));
-      int len = wc + 2 * (hx < W ? hx : W);
-      if (len > W) len = W;
-      int k = (len + 31) >> 5;
-      if ((k & 3) == 0) ++k;
-      pre[r + 1] = pre[r] + env_w0 + k;
-    }
-    const double per_plane = pre[ownN], total = per_plane * planes;
-    S.bound[0] = 0;
-    for (int c = 1; c < grid; ++c) {
-      const double goal = total * c / grid;
-      int pl = (int)(goal / per_plane);
-      if (pl >= planes) pl = planes - 1;
-      const double rem = goal - pl * per_plane;
-      int r = (int)(std::upper_bound(pre.begin(), pre.end(), rem) - pre.begin()) - 1;
-      if (r < 0) r = 0;
-      if (r > ownN) r = ownN;
-      if (r < min_seg) r = 0;
-      else if (ownN - r < min_seg) { r = 0; ++pl; }
-      int b = pl * ownN + r;
-      if (b < S.bound[c - 1]) b = S.bound[c - 1];
-      S.bound[c] = b;
-    }
-    S.bound[grid] = S.total_rows;
-  }
+  rows_partition<INTERP>(P, S, reach, wc, planes, grid);
   kern<<<grid, kRowsWarps * 32, smem, st>>>(P, S);
   {
     const long long nfix = (long long)S.total_rows * nS * (NT - 1);
@@ -1201,6 +1259,52 @@ static int pad_check(const void* a, const void* b, int64_t planes, int H, int W,
   if (H < p + 1 || W < 2 * p) return fail(PARADIS_ERR_BAD_SHAPE, "pad width %d too large for %dx%d", p, H, W);
   if (planes > 65535 || H + 2 * p > 65535) return fail(PARADIS_ERR_BAD_SHAPE, "too many planes/rows for one launch");
   return PARADIS_OK;
+}
+
+// Halo outbox of the latitude-band decomposition: first / last h rows of up to four tensors in one launch.
+struct HaloPackArgs { const float* src[4]; long long sB[4]; };
+
+template <int VEC>
+__global__ void halo_pack_kernel(HaloPackArgs a, int n, int V, int rows, int Wv, int h, float* __restrict__ box, long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long planes_hw = (long long)h * Wv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    // i = (((k * 2 + side) * planes + pl) * h + r) * Wv + x
+    long long q = i / planes_hw;
+    const long long rx = i - q * planes_hw;
+    const int r = (int)(rx / Wv), x = (int)(rx - (long long)r * Wv);
+    const long long planes = total / ((long long)n * 2 * planes_hw);
+    const int pl = (int)(q % planes); q /= planes;
+    const int side = (int)(q & 1), k = (int)(q >> 1);
+    const int b = pl / V, c = pl - b * V;
+    const int row = side ? rows - h + r : r;
+    const float* sp = a.src[k] + b * a.sB[k] + ((long long)c * rows + row) * (Wv * VEC);
+    if (VEC == 4) reinterpret_cast<float4*>(box)[i] = __ldg(reinterpret_cast<const float4*>(sp) + x);
+    else box[i] = __ldg(sp + x);
+  }
+}
+
+extern "C" int paradis_halo_pack(const float* const* src, const int64_t* src_sB, int n, int B, int V, int rows, int W,
+                                 int h, float* box, void* stream) {
+  if (!src || !src_sB || !box) return fail(PARADIS_ERR_NULL_POINTER, "halo_pack: NULL pointer");
+  if (n < 1 || n > 4 || B < 1 || V < 1 || W < 1 || h < 1 || rows < h)
+    return fail(PARADIS_ERR_BAD_SHAPE, "halo_pack: need 1 <= n <= 4 tensors and 1 <= h <= rows (n=%d h=%d rows=%d)", n, h, rows);
+  HaloPackArgs a;
+  bool vec = (W % 4 == 0) && ((uintptr_t)box % 16 == 0);
+  for (int k = 0; k < 4; ++k) {
+    a.src[k] = k < n ? src[k] : nullptr;
+    a.sB[k] = k < n ? (long long)src_sB[k] : 0;
+    if (k < n && !src[k]) return fail(PARADIS_ERR_NULL_POINTER, "halo_pack: NULL tensor pointer");
+    if (k < n && ((uintptr_t)src[k] % 16 != 0 || src_sB[k] % 4 != 0)) vec = false;
+  }
+  const int VEC = vec ? 4 : 1, Wv = W / VEC;
+  const long long total = (long long)n * 2 * B * V * h * Wv;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (vec) halo_pack_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, n, V, rows, Wv, h, box, total);
+  else halo_pack_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, n, V, rows, Wv, h, box, total);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PARADIS_OK : fail(PARADIS_ERR_CUDA, "halo_pack: %s", cudaGetErrorString(e));
 }
 
 extern "C" int paradis_geocyclic_pad_fwd(const float* x, float* y, int64_t planes, int H, int W, int p, void* stream) {

@@ -60,10 +60,13 @@ class BandPlan:
         return (self.row0, self.rows), (self.ext_row0, self.ext_rows)
 
 
-def band_rows(H: int, world: int, cost: Optional[List[float]] = None) -> List[Tuple[int, int]]:
-    """Split H rows into `world` contiguous bands: equal height, or equal total `cost` when a per-row
-    cost is given (rows near the poles are several times more expensive in the backward, see
-    `row_costs`)."""
+def band_rows(H: int, world: int, cost: Optional[List[float]] = None, overhead_rows: float = 0.0,
+              min_rows: int = 1) -> List[Tuple[int, int]]:
+    """Split H rows into `world` contiguous bands: equal height, or -- when a per-row `cost` is given (rows near the
+    poles are several times more expensive in the backward, see `row_costs`) -- the split that levels the bands'
+    costs (dynamic programme over the cut rows), a band of n rows costing  sum(cost) * (1 + overhead_rows / n):  every CTA segment of the row
+    sweep re-plays ring - 1 arrival rows before its first own row, at the latitude it works at, so a band carries
+    a number of extra rows that does not shrink with its height (tools/band_local.py measures it)."""
     if cost is None:
         base, rem = divmod(H, world)
         out, r = [], 0
@@ -72,17 +75,31 @@ def band_rows(H: int, world: int, cost: Optional[List[float]] = None) -> List[Tu
             out.append((r, n))
             r += n
         return out
-    total, out, r, acc = float(sum(cost)), [], 0, 0.0
-    for k in range(world):
-        goal = total * (k + 1) / world
-        start = r
-        while r < H and (r - start < 1 or acc + cost[r] <= goal + 1e-9) and H - r > world - 1 - k:
-            acc += cost[r]
-            r += 1
-        if k == world - 1:
-            r = H
-        out.append((start, r - start))
-    return out
+    import numpy as np
+    S = np.concatenate([[0.0], np.cumsum(np.asarray(cost, dtype=np.float64))])
+    a = np.arange(H + 1)[:, None]
+    b = np.arange(H + 1)[None, :]
+    n = b - a
+    with np.errstate(divide="ignore", invalid="ignore"):
+        C = np.where(n >= max(min_rows, 1), (S[b] - S[a]) * (1.0 + overhead_rows / np.maximum(n, 1)), np.inf)
+    # sum of 8th powers instead of the plain maximum: the same most expensive band to within a row, and the other
+    # bands come out balanced among themselves too (a pure min-max leaves them arbitrary)
+    C = (C / C[0, H]) ** 8
+    dp = C[0].copy()                                  # one band covering rows [0, b)
+    arg = []
+    for _ in range(1, world):
+        M = dp[:, None] + C                           # band [a, b) after the best split of [0, a)
+        arg.append(M.argmin(axis=0))
+        dp = M.min(axis=0)
+    if not np.isfinite(dp[H]):
+        raise ValueError(f"{H} rows cannot be split into {world} bands of at least {min_rows} rows")
+    cuts, e = [H], H
+    for k in range(world - 2, -1, -1):
+        e = int(arg[k][e])
+        cuts.append(e)
+    cuts.append(0)
+    cuts = cuts[::-1]
+    return [(cuts[k], cuts[k + 1] - cuts[k]) for k in range(world)]
 
 
 def row_costs(H: int, W: int, cfl_cells: float, strip: int = 288, base: float = None) -> List[float]:
@@ -91,8 +108,8 @@ def row_costs(H: int, W: int, cfl_cells: float, strip: int = 288, base: float = 
     consumer scans for the row -- its strip plus the longitudinal reach of the row either side, which grows as
     1 / cos(lat) and becomes the whole circle next to the poles."""
     import os
-    if base is None:      # measured on single bands (tools/band_local.py): the bands balance best without a constant term
-        base = float(os.environ.get("PARADIS_SL_BAND_BASE", "0"))
+    if base is None:      # the forward and the producers: about 2.5 scan steps' worth of time per row at C3
+        base = float(os.environ.get("PARADIS_SL_BAND_BASE", "2.5"))
     dphi = math.pi / max(H - 1, 1)
     delta = cfl_cells * dphi
     out = []
@@ -118,9 +135,18 @@ def make_plan(H: int, W: int, rank: int, world: int, cfl_cells: float, interpola
               balance: bool = False) -> BandPlan:
     """`balance=True` sizes the bands by backward cost instead of by height (fewer rows for the ranks
     that own a polar cap)."""
-    bands = band_rows(H, world, row_costs(H, W, cfl_cells) if balance and world > 1 else None)
-    row0, rows = bands[rank]
     halo = halo_rows(cfl_cells, interpolation)
+    if balance and world > 1:
+        import os
+        # (CTAs + planes) / planes segments per plane, each re-playing ring - 1 = 2 ceil(cfl) + stencil rows - 1 rows
+        warm = float(os.environ.get("PARADIS_SL_BAND_WARM", 3.0 * (2 * math.ceil(cfl_cells) + STENCIL_ROWS[interpolation] - 1)))
+        try:
+            bands = band_rows(H, world, row_costs(H, W, cfl_cells), warm, halo + 1)
+        except ValueError:
+            bands = band_rows(H, world)
+    else:
+        bands = band_rows(H, world)
+    row0, rows = bands[rank]
     if world > 1 and min(n for _, n in bands) <= halo:   # strictly thicker: a pole row is never in a neighbour's halo
         raise ValueError(f"bands of {min(n for _, n in bands)} rows are not thicker than the halo ({halo} rows): "
                          "use fewer ranks or a smaller cfl_cells")
@@ -171,76 +197,82 @@ def exchange_rows(x: torch.Tensor, plan: BandPlan, group=None) -> torch.Tensor:
 
 
 class PeerHalo:
-    """Boundary rows of `field` published in NVLink peer memory (torch symmetric memory).
+    """Boundary rows of the band tensors published in NVLink peer memory (torch symmetric memory).
 
-    outbox[0] = this band's first `halo` rows (read by the southern neighbour as ITS northern halo),
-    outbox[1] = this band's last `halo` rows (read by the northern neighbour as its southern halo).
-    `publish(field)` is stream-ordered: barrier (everybody finished reading the previous contents),
-    two small copies, barrier (everybody's rows are in place).  The kernels then dereference
-    `lo_ptr` / `hi_ptr` -- addresses inside the NEIGHBOURS' outboxes -- directly."""
+    box[parity][slot][side]: side 0 = this band's first `halo` rows (read by the southern neighbour as ITS northern
+    halo), side 1 = its last `halo` rows (read by the northern neighbour as its southern halo); slot 0 = field,
+    slots 1..3 = u, v, grad_out of the backward.  A publish is stream-ordered device work: ONE pack kernel
+    (`paradis_halo_pack`) into the outbox of the current parity, then ONE barrier (everybody's rows are in place);
+    the kernels then dereference `lo` / `hi` -- addresses inside the NEIGHBOURS' outboxes -- directly.
+
+    The outbox is double-buffered so that no barrier is needed BEFORE the pack: publish n + 2 overwrites the buffer
+    of publish n, and a rank only gets there after passing the barrier of publish n + 1, which every neighbour
+    reaches after its kernels that read publish n (same stream).  Every rank must publish the same sequence."""
 
     def __init__(self, plan: BandPlan, B: int, V: int, device, group=None, pull_field: bool = False):
         import torch.distributed._symmetric_memory as symm
         self.plan, self.planes = plan, B * V
         h, W = plan.halo, plan.W
-        # slot 0: field; slots 1..3: u, v, grad_out of the backward.  [slot][side][plane][h][W]
-        self.box = symm.empty((4, 2, B * V, h, W), dtype=torch.float32, device=device)
+        self.box = symm.empty((2, 4, 2, B * V, h, W), dtype=torch.float32, device=device)
         self.hdl = symm.rendezvous(self.box, group=group if group is not None else dist.group.WORLD)
         side_elems = B * V * h * W
         side_bytes = side_elems * 4
+        self._side_elems = side_elems
         ptrs = self.hdl.buffer_ptrs
         south = int(ptrs[plan.rank - 1]) if plan.rank > 0 else 0
         north = int(ptrs[plan.rank + 1]) if plan.rank < plan.world - 1 else 0
         # my southern halo = the southern neighbour's LAST rows (its side 1); northern halo = side 0 of the northern one
-        self.lo = [south + (2 * k + 1) * side_bytes if south else 0 for k in range(4)]
-        self.hi = [north + (2 * k) * side_bytes if north else 0 for k in range(4)]
+        self._lo = [[south + ((8 * par) + 2 * k + 1) * side_bytes if south else 0 for k in range(4)] for par in range(2)]
+        self._hi = [[north + ((8 * par) + 2 * k) * side_bytes if north else 0 for k in range(4)] for par in range(2)]
+        self.parity = 1                       # parity of the LAST publish (the first one uses 0)
         # pull_field=True: the `field` halo rows are PULLED into local memory right after the publish barrier (one
         # peer-memory copy per side over NVLink, no NCCL) instead of being read in place by the stencil taps.  Measured
         # at N=2: forward 0.238 -> 0.227 ms, backward unchanged, step 1.381 -> 1.407 ms (the copies cost more than the
         # remote taps): off by default.  The u / v / grad_out halo rows of the backward are streamed in place by the
         # row-sweep kernel's TMA bulk copies either way.
         self.local = None
-        self._peer_views = (None, None)
+        self._peer_views = None
         if pull_field:
             self.local = torch.empty((2, B * V, h, W), dtype=torch.float32, device=device)
             shape = (B * V, h, W)
-            lo_view = self.hdl.get_buffer(plan.rank - 1, shape, torch.float32, 1 * side_elems) if south else None
-            hi_view = self.hdl.get_buffer(plan.rank + 1, shape, torch.float32, 0) if north else None
-            self._peer_views = (lo_view, hi_view)
-            self.lo_ptr = self.local[0].data_ptr() if south else 0
-            self.hi_ptr = self.local[1].data_ptr() if north else 0
-        else:
-            self.lo_ptr, self.hi_ptr = self.lo[0], self.hi[0]
+            self._peer_views = [
+                (self.hdl.get_buffer(plan.rank - 1, shape, torch.float32, (8 * par + 1) * side_elems) if south else None,
+                 self.hdl.get_buffer(plan.rank + 1, shape, torch.float32, (8 * par) * side_elems) if north else None)
+                for par in range(2)]
+            self._local_ptrs = (self.local[0].data_ptr() if south else 0, self.local[1].data_ptr() if north else 0)
 
-    def _put(self, slot: int, t: torch.Tensor) -> None:
-        h, W, n = self.plan.halo, self.plan.W, self.plan.rows
-        self.box[slot, 0].copy_(t[:, :, :h].reshape(self.planes, h, W))
-        self.box[slot, 1].copy_(t[:, :, n - h:].reshape(self.planes, h, W))
+    @property
+    def lo(self):
+        return self._lo[self.parity]
 
-    def _pull_field(self) -> None:
-        if self.local is None:
-            return
-        for k, view in enumerate(self._peer_views):
-            if view is not None:
-                self.local[k].copy_(view)
+    @property
+    def hi(self):
+        return self._hi[self.parity]
+
+    def _publish(self, tensors) -> None:
+        from .ops import halo_pack
+        t0 = tensors[0]
+        assert t0.shape[2] == self.plan.rows and t0.shape[0] * t0.shape[1] == self.planes
+        self.parity ^= 1
+        halo_pack([t if t.stride(3) == 1 and t.stride(2) == t.shape[3] and t.stride(1) == t.shape[2] * t.shape[3]
+                   else t.contiguous() for t in tensors], self.box[self.parity], self.plan.halo)
+        self.hdl.barrier(channel=0)
+        if self.local is not None:
+            for k, view in enumerate(self._peer_views[self.parity]):
+                if view is not None:
+                    self.local[k].copy_(view)
 
     def publish(self, field: torch.Tensor) -> None:
-        assert field.shape[2] == self.plan.rows and field.shape[0] * field.shape[1] == self.planes
-        self.hdl.barrier(channel=0)
-        self._put(0, field)
-        self.hdl.barrier(channel=0)
-        self._pull_field()
+        self._publish([field])
 
     def publish_backward(self, field: torch.Tensor, u: torch.Tensor, v: torch.Tensor, g: torch.Tensor) -> None:
-        """One barrier pair for all four tensors of the backward."""
-        self.hdl.barrier(channel=0)
-        for slot, t in enumerate((field, u, v, g)):
-            self._put(slot, t)
-        self.hdl.barrier(channel=0)
-        self._pull_field()
+        """One pack and one barrier for all four tensors of the backward."""
+        self._publish([field, u, v, g])
 
     def peer(self):
-        return (self.lo_ptr, self.hi_ptr, self.plan.halo)
+        if self.local is not None:
+            return (self._local_ptrs[0], self._local_ptrs[1], self.plan.halo)
+        return (self.lo[0], self.hi[0], self.plan.halo)
 
     def arr_peer(self):
         return (self.lo[1:4], self.hi[1:4], self.plan.halo)
@@ -284,6 +316,32 @@ class _LatBandFn(torch.autograd.Function):
                                                           _lib.INTERP[interp], pole_fix, _lib.MATH[math], g.windows,
                                                           cfl, True, True)
         return gf, gu, gv, None, None, None, None, None, None, None, None, None
+
+
+class BandKernels:
+    """The raw (no autograd, preallocated) forward / backward of one band, one pair per outbox parity: the peer
+    addresses a kernel reads depend on which half of the double-buffered outbox the last publish filled."""
+
+    def __init__(self, geometry, plan: BandPlan, peer: "PeerHalo", B: int, V: int, interp: str, math: str, cfl: float):
+        self.args = (geometry, plan, peer, B, V, interp, math, cfl)
+        self._k = {}
+
+    def _get(self, kind: str):
+        from .ops import RawAdvection
+        geometry, plan, peer, B, V, interp, math, cfl = self.args
+        key = (kind, peer.parity)
+        if key not in self._k:
+            own, ext = plan.windows()
+            g = (geometry.band(own, own, own, peer.peer()) if kind == "f"
+                 else geometry.band(own, ext, own, peer.peer(), peer.arr_peer()))
+            self._k[key] = RawAdvection(g, B, V, interp, True, math, cfl)
+        return self._k[key]
+
+    def forward(self, field, u, v, dt):
+        return self._get("f").forward(field, u, v, dt)
+
+    def backward(self, go, field, u, v, dt, phases=3):
+        return self._get("b").backward(go, field, u, v, dt, phases)
 
 
 def lat_band_advect(field, u, v, geometry, plan: BandPlan, dt: float, interpolation="bilinear", pole_fix=True,
@@ -343,17 +401,13 @@ def bench_latband(args, workload, rank, world, dev):
         # symmetric-memory barriers -- is stream-ordered device work: capture it once in a CUDA graph and
         # replay it, which removes the host launch overhead that dominates thin bands.
         try:
-            from .ops import RawAdvection
-            own, ext = plan.windows()
-            Rf = RawAdvection(geo.band(own, own, own, peer.peer()), Bg, V, args.interp, True, args.math, CFL_CELLS)
-            Rb = RawAdvection(geo.band(own, ext, own, peer.peer(), peer.arr_peer()), Bg, V, args.interp, True,
-                              args.math, CFL_CELLS)
+            K = BandKernels(geo, plan, peer, Bg, V, args.interp, args.math, CFL_CELLS)
 
-            def raw_step():
+            def raw_step():                 # two publishes: the outbox parity is the same at the start of every step
                 peer.publish(field)
-                Rf.forward(field, u, v, dt)
+                K.forward(field, u, v, dt)
                 peer.publish_backward(field, u, v, go)
-                Rb.backward(go, field, u, v, dt, 3)
+                K.backward(go, field, u, v, dt, 3)
 
             for _ in range(3):
                 raw_step()
@@ -395,15 +449,11 @@ def bench_latband(args, workload, rank, world, dev):
     ms_step = float(t.item()) / args.steps
 
     # ---- the two phases of a band, timed separately on every rank (eager C-ABI calls; max over ranks)
-    from .ops import RawAdvection
-    own, ext = plan.windows()
     if peer is not None:
-        Rf = RawAdvection(geo.band(own, own, own, peer.peer()), Bg, V, args.interp, True, args.math, CFL_CELLS)
-        Rb = RawAdvection(geo.band(own, ext, own, peer.peer(), peer.arr_peer()), Bg, V, args.interp, True, args.math,
-                          CFL_CELLS)
+        K2 = BandKernels(geo, plan, peer, Bg, V, args.interp, args.math, CFL_CELLS)
         phase = []
-        for fn, pub in ((lambda: Rf.forward(field, u, v, dt), lambda: peer.publish(field)),
-                        (lambda: Rb.backward(go, field, u, v, dt, 3), lambda: peer.publish_backward(field, u, v, go))):
+        for fn, pub in ((lambda: K2.forward(field, u, v, dt), lambda: peer.publish(field)),
+                        (lambda: K2.backward(go, field, u, v, dt, 3), lambda: peer.publish_backward(field, u, v, go))):
             pub(); fn()
             torch.cuda.synchronize(); dist.barrier()
             n_ph = max(3, min(args.steps, 10))
@@ -509,7 +559,7 @@ def bench_latband(args, workload, rank, world, dev):
             "collective": {"kind": "none (NCCL is only used for rendezvous and the timing all-reduce)" if peer is not None
                            else "NCCL send/recv (batch_isend_irecv)",
                            "data_path": transport, "halo_bytes_per_rank_per_tensor": halo_bytes,
-                           "barriers_per_step": 4 if peer is not None else 0},
+                           "barriers_per_step": 2 if peer is not None else 0},
             "clocks": clocks, "gpu_launches": 12 * args.steps}
         if e2e:
             line["e2e"] = e2e

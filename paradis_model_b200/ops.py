@@ -516,6 +516,32 @@ def geocyclic_avgpool5(x: Tensor, stride: int) -> Tensor:
     return torch.ops.paradis.geocyclic_avgpool5(x, int(stride))
 
 
+# --------------------------------------------------------------------------------------
+# halo_pack: boundary rows of the band tensors into the symmetric-memory outbox (halo.PeerHalo), one launch
+# --------------------------------------------------------------------------------------
+@torch.library.custom_op("paradis::halo_pack", mutates_args=("box",), device_types="cuda")
+def _halo_pack(xs: List[Tensor], box: Tensor, h: int) -> None:
+    import ctypes as C
+    n = len(xs)
+    B, V, rows, W = xs[0].shape
+    for t in xs:
+        if (t.dtype != torch.float32 or tuple(t.shape) != (B, V, rows, W) or t.stride(3) != 1 or t.stride(2) != W
+                or t.stride(1) != rows * W):
+            raise RuntimeError("halo_pack expects fp32 [B, V, rows, W] tensors whose inner three dims are contiguous")
+    if box.dtype != torch.float32 or not box.is_contiguous() or box.numel() < n * 2 * B * V * h * W:
+        raise RuntimeError("halo_pack: outbox too small or not contiguous fp32")
+    src = (C.c_void_p * n)(*[t.data_ptr() for t in xs])
+    sB = (C.c_int64 * n)(*[t.stride(0) if B > 1 else V * rows * W for t in xs])
+    with torch.cuda.device(box.device):
+        rc = _lib.lib().paradis_halo_pack(src, sB, n, B, V, rows, W, h, _ptr(box), _stream(box))
+    _lib.check(rc, "paradis_halo_pack")
+
+
+def halo_pack(xs: List[Tensor], box: Tensor, h: int) -> None:
+    """First and last `h` rows of every tensor of `xs` ([B, V, rows, W]) -> box[len(xs)][2][B*V][h][W]."""
+    torch.ops.paradis.halo_pack(list(xs), box, int(h))
+
+
 def geocyclic_dwconv(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
     """``depthwise_conv(GeoCyclicPadding((k-1)//2)(x))`` in one kernel (k = 3, 5, 7): drop-in for the first
     two lines of SepConv.forward (model/blocks.py:112-114).  Differentiable w.r.t. x, weight and bias."""

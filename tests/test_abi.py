@@ -24,7 +24,7 @@ def test_library_builds_and_loads():
 
 def test_exports_every_declared_symbol():
     names = header_functions()
-    assert len(names) == 16
+    assert len(names) == 17
     handle = C.CDLL(build.build_library())
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/paradis_sl.h but not exported"

@@ -775,3 +775,25 @@ def test_physical_downsample_strided_kernel(stride):
 def test_dwconv_rejects_meshes_where_both_caps_fold_onto_one_row():
     with pytest.raises(RuntimeError, match="mesh too small"):
         P().geocyclic_dwconv(torch.zeros(1, 2, 5, 16, device="cuda"), torch.zeros(2, 1, 5, 5, device="cuda"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W", [64, 30])
+def test_halo_pack_matches_slices(W):
+    """paradis_halo_pack: first / last h rows of several band tensors (one of them a strided channel view) into
+    box[n][2][planes][h][W] in one launch -- compared with plain slicing."""
+    from paradis_model_b200.ops import halo_pack
+    B, V, rows, h = 2, 3, 17, 5
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(B, V, rows, W, generator=g).cuda()
+    uv = torch.randn(B, 2 * V, rows, W, generator=g).cuda()
+    u, v = uv[:, :V], uv[:, V:]                       # model/paradis.py:235-237: views of one tensor
+    box = torch.full((2, 3, 2, B * V, h, W), -7.0, device="cuda")
+    halo_pack([a, u, v], box[1], h)
+    torch.cuda.synchronize()
+    for k, t in enumerate((a, u, v)):
+        assert torch.equal(box[1, k, 0], t[:, :, :h].reshape(B * V, h, W))
+        assert torch.equal(box[1, k, 1], t[:, :, rows - h:].reshape(B * V, h, W))
+    assert bool((box[0] == -7.0).all())
+    with pytest.raises(RuntimeError):
+        halo_pack([a.transpose(2, 3)], box[0], h)

@@ -77,4 +77,16 @@ def test_band_rows_and_plan():
     assert bands[0][0] == 0 and sum(n for _, n in bands) == 721
     assert all(bands[k][0] + bands[k][1] == bands[k + 1][0] for k in range(7))
     assert bands[0][1] < bands[3][1] and bands[7][1] < bands[4][1]
-    assert halo.make_plan(721, 1440, 0, 8, 6.0, balance=True).rows == bands[0][1]
+    # make_plan adds the per-band warm-up overhead and the minimum thickness (halo + 1 rows): symmetric, polar bands thinner still
+    plans = [halo.make_plan(721, 1440, r, 8, 6.0, balance=True) for r in range(8)]
+    assert sum(p.rows for p in plans) == 721 and all(p.rows > p.halo for p in plans)
+    assert plans[0].rows <= bands[0][1] and abs(plans[0].rows - plans[7].rows) <= 1
+    assert abs(plans[3].rows - plans[4].rows) <= 1
+    # the levelled split never has a band more expensive than the equal-height split's most expensive one
+    S = [0.0]
+    for c in cost:
+        S.append(S[-1] + c)
+    worst = lambda bs: max(S[a + n] - S[a] for a, n in bs)
+    assert worst(bands) <= worst(halo.band_rows(721, 8))
+    with pytest.raises(ValueError):
+        halo.band_rows(20, 4, [1.0] * 20, 0.0, 6)
