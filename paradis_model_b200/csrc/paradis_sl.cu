@@ -910,7 +910,7 @@ struct RowsPartEntry { RowsPartKey key; int bound[kRowsMaxCtas + 1]; bool valid;
 template <int INTERP>
 static void rows_partition(const Params& P, RowsPlan& S, const ReachModel& reach, int wc, int planes, int grid) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
-  static const int env_w0 = env_int("PARADIS_SL_ROWS_W0", 6);
+  static const int env_w0 = env_int("PARADIS_SL_ROWS_W0", 4);
   static const int env_wcore = env_int("PARADIS_SL_ROWS_WCORE", 0);   // extra cost of a row whose grad_u / grad_v the segment writes
   static thread_local RowsPartEntry cache[8];
   static thread_local int cache_next = 0;
@@ -1005,7 +1005,7 @@ static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const
   memset(&S, 0, sizeof(S));
   S.planes = planes; S.rr = rr; S.ring = 2 * rr + NT;
   static const int env_nc = env_int("PARADIS_SL_ROWS_NC", 0);
-  int nC = env_nc > 0 ? env_nc : (INTERP == 1 ? 5 : 8);
+  int nC = env_nc > 0 ? env_nc : (INTERP == 1 ? 6 : 8);
   if (nC > kRowsMaxConsumers) nC = kRowsMaxConsumers;
   int nS = nC * kStreams;                                  // strips: kStreams per consumer warp
   int wc = ((W + nS - 1) / nS + 3) & ~3;

@@ -102,7 +102,7 @@ def band_rows(H: int, world: int, cost: Optional[List[float]] = None, overhead_r
     return [(cuts[k], cuts[k + 1] - cuts[k]) for k in range(world)]
 
 
-def row_costs(H: int, W: int, cfl_cells: float, strip: int = 288, base: float = None) -> List[float]:
+def row_costs(H: int, W: int, cfl_cells: float, strip: int = 240, base: float = None) -> List[float]:
     """Relative backward cost of a row on a pole-to-pole mesh, the model the row-sweep kernel balances its own CTAs
     with (csrc/paradis_sl.cu, launch_rows): a constant for the producers plus the number of 32-record steps a
     consumer scans for the row -- its strip plus the longitudinal reach of the row either side, which grows as
