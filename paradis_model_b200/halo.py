@@ -562,7 +562,7 @@ def bench_latband(args, workload, rank, world, dev):
                            else "NCCL send/recv (batch_isend_irecv)",
                            "data_path": transport, "halo_bytes_per_rank_per_tensor": halo_bytes,
                            "barriers_per_step": 2 if peer is not None else 0},
-            "clocks": clocks, "gpu_launches": 12 * args.steps}
+            "clocks": clocks, "gpu_launches": (12 + (2 if peer is not None else 0)) * args.steps}
         if e2e:
             line["e2e"] = e2e
         if batch:
