@@ -911,6 +911,7 @@ template <int INTERP>
 static void rows_partition(const Params& P, RowsPlan& S, const ReachModel& reach, int wc, int planes, int grid) {
   constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
   static const int env_w0 = env_int("PARADIS_SL_ROWS_W0", 4);
+  static const double env_capw = env_int("PARADIS_SL_ROWS_CAPW100", 100) / 100.0;   // weight of the whole-circle rows
   static const int env_wcore = env_int("PARADIS_SL_ROWS_WCORE", 0);   // extra cost of a row whose grad_u / grad_v the segment writes
   static thread_local RowsPartEntry cache[8];
   static thread_local int cache_next = 0;
@@ -933,7 +934,7 @@ static void rows_partition(const Params& P, RowsPlan& S, const ReachModel& reach
     if (len > W) len = W;
     int k = (len + 31) >> 5;
     if ((k & 3) == 0) ++k;
-    A[y + 1] = A[y] + env_w0 + k;
+    A[y + 1] = A[y] + env_w0 + (len >= W ? k * env_capw : (double)k);
   }
   const int arr_lo = P.arr0, arr_hi = P.arr0 + P.arrN;
   auto seg_cost = [&](int ra, int rb) {                     // destination rows [ra, rb) (global) of one plane
@@ -1044,8 +1045,10 @@ static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const
   rows_prep_kernel<<<(nprep + 255) / 256, 256, 0, st>>>(P.sin_lat, P.cos_lat, H, reach, hx_tab, flag, planes);
   S.hx_tab = hx_tab; S.plane_flag = flag; S.out0 = P.own0; S.outN = P.ownN;
   S.guard = (float*)(ws + L.guard);
-  static const int env_rows = env_int("PARADIS_SL_ROWS_PER_CTA", 24);
-  int grid = S.total_rows / (env_rows > 0 ? env_rows : 24);
+  // one CTA per SM unless that leaves a CTA fewer than ~12 own rows (a ring warm-up is ring - 1 rows).  The floor was 24
+  // at first: the 47-row polar band of the 8-way split then ran on 125 of the 148 SMs (backward 0.38 instead of 0.32 ms)
+  static const int env_rows = env_int("PARADIS_SL_ROWS_PER_CTA", 12);
+  int grid = S.total_rows / (env_rows > 0 ? env_rows : 12);
   if (grid < 1) grid = 1;
   if (grid > nsm) grid = nsm;
   if (grid > kRowsMaxCtas) grid = kRowsMaxCtas;

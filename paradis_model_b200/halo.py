@@ -110,6 +110,7 @@ def row_costs(H: int, W: int, cfl_cells: float, strip: int = 240, base: float = 
     import os
     if base is None:      # the forward and the producers: about 2.5 scan steps' worth of time per row at C3
         base = float(os.environ.get("PARADIS_SL_BAND_BASE", "2.5"))
+    capw = float(os.environ.get("PARADIS_SL_BAND_CAPW", "1.0"))     # weight of the rows that scan the whole circle
     dphi = math.pi / max(H - 1, 1)
     delta = cfl_cells * dphi
     out = []
@@ -121,7 +122,7 @@ def row_costs(H: int, W: int, cfl_cells: float, strip: int = 240, base: float = 
             if sdl < 1.0:
                 cells = min(W, math.asin(sdl) / (2 * math.pi / W) + 4)
         scan = min(W, strip + 2 * cells)
-        out.append(base + math.ceil(scan / 32))
+        out.append(base + math.ceil(scan / 32) * (capw if scan >= W else 1.0))
     return out
 
 
