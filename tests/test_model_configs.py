@@ -169,16 +169,21 @@ def test_inductor_compiled_reference_is_the_comparator():
             ref_fn(a, b, c).backward(g)
 
         def timed(fn, n):
+            # best of three batches: the small case is launch-bound on every arm, and one run of this test landed on
+            # a busy host (all three C2 arms 1.2-3.7x slower than in the runs before and after)
             for _ in range(2):
                 fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(n):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / n
+            best = float("inf")
+            for _ in range(3):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) / n)
+            return best
 
         res[name] = {"workload": f"{H}x{W} V={V} B={B} bilinear fwd+bwd", "torch_eager_ms": timed(eager, 3),
                      "torch_inductor_ms": timed(compiled, 5), "paradis_model_b200_ms": timed(ours, 10)}
