@@ -51,6 +51,7 @@ def parse():
                     help="N>1: latitude bands of ONE global problem (strong scaling; default for c3) or one replica "
                          "per GPU (weak scaling)")
     ap.add_argument("--no-batch", action="store_true", help="latband: skip the batch-sharded comparison leg")
+    ap.add_argument("--pull-all", action="store_true", help="lat bands: pull the halo rows of all four tensors into local buffers")
     ap.add_argument("--pull-field", action="store_true",
                     help="latband: pull the neighbours' field rows into a local buffer after the publish barrier instead of "
                          "reading them in place with the stencil taps (measured: no gain)")

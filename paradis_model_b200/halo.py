@@ -210,7 +210,8 @@ class PeerHalo:
     of publish n, and a rank only gets there after passing the barrier of publish n + 1, which every neighbour
     reaches after its kernels that read publish n (same stream).  Every rank must publish the same sequence."""
 
-    def __init__(self, plan: BandPlan, B: int, V: int, device, group=None, pull_field: bool = False):
+    def __init__(self, plan: BandPlan, B: int, V: int, device, group=None, pull_field: bool = False,
+                 pull_all: bool = False):
         import torch.distributed._symmetric_memory as symm
         self.plan, self.planes = plan, B * V
         h, W = plan.halo, plan.W
@@ -226,29 +227,42 @@ class PeerHalo:
         self._lo = [[south + ((8 * par) + 2 * k + 1) * side_bytes if south else 0 for k in range(4)] for par in range(2)]
         self._hi = [[north + ((8 * par) + 2 * k) * side_bytes if north else 0 for k in range(4)] for par in range(2)]
         self.parity = 1                       # parity of the LAST publish (the first one uses 0)
-        # pull_field=True: the `field` halo rows are PULLED into local memory right after the publish barrier (one
-        # peer-memory copy per side over NVLink, no NCCL) instead of being read in place by the stencil taps.  Measured
-        # at N=2: forward 0.238 -> 0.227 ms, backward unchanged, step 1.381 -> 1.407 ms (the copies cost more than the
-        # remote taps): off by default.  The u / v / grad_out halo rows of the backward are streamed in place by the
-        # row-sweep kernel's TMA bulk copies either way.
+        # pull_field / pull_all: the halo rows (of `field` only / of all published tensors) are PULLED into local memory
+        # right after the publish barrier -- one strided peer-memory copy per side over NVLink, no NCCL -- instead of
+        # being read in place by the stencil taps and the TMA bulk copies of the kernels.  Thick bands (N=2) are faster
+        # in place (the copies cost more than the remote accesses they save); thin bands pay relatively more for the
+        # NVLink latency inside the kernels.  See DESIGN section 5 for the measurements.
         self.local = None
         self._peer_views = None
-        if pull_field:
-            self.local = torch.empty((2, B * V, h, W), dtype=torch.float32, device=device)
-            shape = (B * V, h, W)
-            self._peer_views = [
-                (self.hdl.get_buffer(plan.rank - 1, shape, torch.float32, (8 * par + 1) * side_elems) if south else None,
-                 self.hdl.get_buffer(plan.rank + 1, shape, torch.float32, (8 * par) * side_elems) if north else None)
-                for par in range(2)]
-            self._local_ptrs = (self.local[0].data_ptr() if south else 0, self.local[1].data_ptr() if north else 0)
+        self._pull_slots = 4 if pull_all else (1 if pull_field else 0)
+        if self._pull_slots:
+            ns = self._pull_slots
+            self.local = torch.empty((2, 4, B * V, h, W), dtype=torch.float32, device=device)   # [side][slot]
+            full = (2, 4, 2, B * V, h, W)
+            views = []
+            for par in range(2):
+                lo_v = self.hdl.get_buffer(plan.rank - 1, full, torch.float32, 0)[par, :, 1] if south else None
+                hi_v = self.hdl.get_buffer(plan.rank + 1, full, torch.float32, 0)[par, :, 0] if north else None
+                views.append((lo_v, hi_v))
+            self._peer_views = views
+            loc = [[self.local[sd, k].data_ptr() for k in range(4)] for sd in range(2)]
+            self._lo_local = [loc[0][k] if (south and k < ns) else None for k in range(4)]
+            self._hi_local = [loc[1][k] if (north and k < ns) else None for k in range(4)]
 
     @property
     def lo(self):
-        return self._lo[self.parity]
+        """Addresses of this band's southern halo rows, one per slot: inside the neighbour's outbox, or local if pulled."""
+        p = self._lo[self.parity]
+        if self.local is None:
+            return p
+        return [self._lo_local[k] if self._lo_local[k] is not None else p[k] for k in range(4)]
 
     @property
     def hi(self):
-        return self._hi[self.parity]
+        p = self._hi[self.parity]
+        if self.local is None:
+            return p
+        return [self._hi_local[k] if self._hi_local[k] is not None else p[k] for k in range(4)]
 
     def _publish(self, tensors) -> None:
         from .ops import halo_pack
@@ -259,9 +273,10 @@ class PeerHalo:
                    else t.contiguous() for t in tensors], self.box[self.parity], self.plan.halo)
         self.hdl.barrier(channel=0)
         if self.local is not None:
-            for k, view in enumerate(self._peer_views[self.parity]):
+            n = min(len(tensors), self._pull_slots)            # slots this publish filled (1: field, 4: backward)
+            for sd, view in enumerate(self._peer_views[self.parity]):
                 if view is not None:
-                    self.local[k].copy_(view)
+                    self.local[sd, :n].copy_(view[:n])
 
     def publish(self, field: torch.Tensor) -> None:
         self._publish([field])
@@ -271,8 +286,6 @@ class PeerHalo:
         self._publish([field, u, v, g])
 
     def peer(self):
-        if self.local is not None:
-            return (self._local_ptrs[0], self._local_ptrs[1], self.plan.halo)
         return (self.lo[0], self.hi[0], self.plan.halo)
 
     def arr_peer(self):
@@ -381,11 +394,16 @@ def bench_latband(args, workload, rank, world, dev):
     peer, transport = None, "NCCL send/recv for field, grad_out, u, v"
     if not getattr(args, "no_p2p", False):
         try:
-            peer = PeerHalo(plan, Bg, V, dev, pull_field=getattr(args, "pull_field", False))
-            transport = ("halos over NVLink peer memory (symmetric memory), no NCCL on the data path: u, v, grad_out rows streamed in "
-                         "place by TMA bulk copies inside the backward kernel, field rows "
-                         + ("pulled into a local buffer by one peer copy per side after the publish barrier"
-                            if getattr(args, "pull_field", False) else "read in place by the stencil taps"))
+            peer = PeerHalo(plan, Bg, V, dev, pull_field=getattr(args, "pull_field", False),
+                            pull_all=getattr(args, "pull_all", False))
+            if getattr(args, "pull_all", False):
+                transport = ("halos over NVLink peer memory (symmetric memory), no NCCL on the data path: the boundary rows of field, "
+                             "u, v, grad_out are pulled into local buffers by one strided peer copy per side after the publish barrier")
+            else:
+                transport = ("halos over NVLink peer memory (symmetric memory), no NCCL on the data path: u, v, grad_out rows streamed in "
+                             "place by TMA bulk copies inside the backward kernel, field rows "
+                             + ("pulled into a local buffer by one peer copy per side after the publish barrier"
+                                if getattr(args, "pull_field", False) else "read in place by the stencil taps"))
         except Exception as exc:   # symmetric memory unavailable: NCCL transport for everything
             transport += f" (symmetric memory unavailable: {type(exc).__name__})"
 
