@@ -735,7 +735,8 @@ extern "C" int paradis_sl_advect_fwd(const paradis_sl_geom* geom, const float* f
 
 // workspace layout (backward): fmean | gmean | plane_reach[3] | plane_flag | hx | guard | blkmax[3] | cls
 // (three reach / blkmax sets: the two polar caps run concurrently with the sweep, then the fallback)
-struct BwdWs { size_t fmean, gmean, reach, reach_stride, flag, hx, guard, blkmax, blkmax_stride, cls, total; int nblk; };
+struct BwdWs { size_t fmean, gmean, reach, reach_stride, flag, hx, guard, grow, grow_bytes, blkmax, blkmax_stride, cls, total; int nblk; };
+constexpr int kRowsMaxGuardRows = 14;   // cut mode of the rows kernel up to rr + NT = 14 (cfl hint <= 10 cells)
 static BwdWs bwd_layout(int B, int V, int arr_rows, int W) {
   BwdWs w;
   const size_t planes = (size_t)B * V;
@@ -750,6 +751,9 @@ static BwdWs bwd_layout(int B, int V, int arr_rows, int W) {
   w.hx = off; off += 65536 * sizeof(int);          // longitudinal reach per arrival row (rows kernel)
   // guard columns of the rows kernel: [planes][rows][consumers][NT - 1]
   w.guard = off; off += align_up(planes * (size_t)arr_rows * kRowsWarps * kStreams * 3 * sizeof(float), 256);
+  // partial destination rows either side of the cuts of the rows kernel: [CTAs][2][GR][strips * pitch]
+  w.grow_bytes = align_up((size_t)kRowsMaxCtas * 2 * kRowsMaxGuardRows * ((size_t)W + 256) * sizeof(float), 256);
+  w.grow = off; off += w.grow_bytes;
   w.blkmax_stride = align_up(planes * (size_t)w.nblk, 256);
   w.blkmax = off; off += 3 * w.blkmax_stride;
   w.cls = off; off += align_up(planes * (size_t)arr_rows * W, 256);
@@ -905,7 +909,7 @@ static int env_int(const char* name, int dflt) {
 // onto plane boundaries: 5 % slower at C3, 11-22 % on thin latitude bands.  Only balance depends on the model.
 // The result is cached per shape (it costs ~1 ms of host time).
 struct RowsPartKey { long long v[14]; };
-struct RowsPartEntry { RowsPartKey key; int bound[kRowsMaxCtas + 1]; bool valid; };
+struct RowsPartEntry { RowsPartKey key; int bound[kRowsMaxCtas + 1]; int cut; bool valid; };
 
 template <int INTERP>
 static void rows_partition(const Params& P, RowsPlan& S, const ReachModel& reach, int wc, int planes, int grid) {
@@ -920,10 +924,10 @@ static void rows_partition(const Params& P, RowsPlan& S, const ReachModel& reach
   const int H = P.H, W = P.W, ownN = P.ownN;
   int fbits[2];
   memcpy(&fbits[0], &P.min_lat, 4); memcpy(&fbits[1], &P.d_lat, 4);
-  const long long kv[14] = {H, W, planes, P.own0, ownN, P.arr0, P.arrN, S.rr, NT, wc, grid, env_w0, fbits[0], fbits[1]};
+  const long long kv[14] = {H, W, planes, P.own0, ownN, P.arr0, P.arrN, S.rr + 1000 * S.cut, NT, wc, grid, env_w0, fbits[0], fbits[1]};
   memcpy(key.v, kv, sizeof(kv));
   for (auto& e : cache)
-    if (e.valid && memcmp(&e.key, &key, sizeof(key)) == 0) { memcpy(S.bound, e.bound, sizeof(S.bound)); return; }
+    if (e.valid && memcmp(&e.key, &key, sizeof(key)) == 0) { memcpy(S.bound, e.bound, sizeof(S.bound)); S.cut = e.cut; return; }
 
   const double dphi = (double)P.d_lat / (H - 1);
   std::vector<double> A(H + 1, 0.0);                       // prefix of the arrival-row costs over global rows
@@ -938,10 +942,14 @@ static void rows_partition(const Params& P, RowsPlan& S, const ReachModel& reach
   }
   const int arr_lo = P.arr0, arr_hi = P.arr0 + P.arrN;
   auto seg_cost = [&](int ra, int rb) {                     // destination rows [ra, rb) (global) of one plane
-    int y0 = ra - (S.ring - 1) + S.rr - OMIN, y1 = rb - 1 + S.rr - OMIN;
+    // cut mode: a segment that starts / ends inside the plane processes its own arrival rows only and stores the
+    // partial rows beyond the cut (about the cost of retiring as many own rows)
+    const bool cut_lo = S.cut && ra > P.own0, cut_hi = S.cut && rb < P.own0 + ownN;
+    int y0 = cut_lo ? ra : ra - (S.ring - 1) + S.rr - OMIN, y1 = cut_hi ? rb - 1 : rb - 1 + S.rr - OMIN;
     if (y0 < arr_lo) y0 = arr_lo;
     if (y1 > arr_hi - 1) y1 = arr_hi - 1;
-    return (y1 >= y0 ? A[y1 + 1] - A[y0] : 0.0) + (double)env_wcore * (rb - ra);
+    return (y1 >= y0 ? A[y1 + 1] - A[y0] : 0.0) + (double)env_wcore * (rb - ra) +
+           (double)env_w0 * S.GR * ((cut_lo ? 1 : 0) + (cut_hi ? 1 : 0));
   };
   const long long total = (long long)planes * ownN;
   const double plane_cost = seg_cost(P.own0, P.own0 + ownN);
@@ -958,6 +966,8 @@ static void rows_partition(const Params& P, RowsPlan& S, const ReachModel& reach
         const int mid = (lo + hi + 1) >> 1;
         if (used + seg_cost(P.own0 + r, P.own0 + mid) <= T) lo = mid; else hi = mid - 1;
       }
+      // cut mode: two cuts inside one plane stay at least GR rows apart (rows_grow_fix_kernel: one source per element)
+      if (S.cut && r > 0 && used == 0.0 && lo < ownN && lo - r < S.GR) lo = r + S.GR < ownN ? r + S.GR : ownN;
       if (lo == r) break;
       used += seg_cost(P.own0 + r, P.own0 + lo);
       e += lo - r;
@@ -988,14 +998,41 @@ static void rows_partition(const Params& P, RowsPlan& S, const ReachModel& reach
     S.bound[c] = (int)b;
   }
   S.bound[grid] = (int)total;
+  if (S.cut) {
+    // safety net of the cut mode: two cuts of one plane closer than GR rows -> partition again without cuts
+    bool ok = true;
+    int prev = -1;
+    for (int c = 1; c < grid && ok; ++c) {
+      const int gcut = S.bound[c];
+      if (gcut % ownN == 0 || gcut == prev) continue;
+      if (prev >= 0 && prev / ownN == gcut / ownN && gcut - prev < S.GR) ok = false;
+      prev = gcut;
+    }
+    if (!ok) {
+      S.cut = 0;
+      rows_partition<INTERP>(P, S, reach, wc, planes, grid);        // (cached under its own key)
+    }
+  }
+  static const int env_dump = env_int("PARADIS_SL_ROWS_DUMP", 0);
+  if (env_dump) {
+    int ncut = 0, minlen = 1 << 30, maxlen = 0, used = 0;
+    for (int c = 0; c < grid; ++c) {
+      const int n = S.bound[c + 1] - S.bound[c];
+      if (n <= 0) continue;
+      ++used; if (n < minlen) minlen = n; if (n > maxlen) maxlen = n;
+      if (S.bound[c + 1] % ownN != 0) ++ncut;
+    }
+    fprintf(stderr, "[paradis_sl] rows partition: %d of %d CTAs, %d cuts, rows per CTA %d..%d, cut mode %d, budget %.0f\n",
+            used, grid, ncut, minlen, maxlen, S.cut, hi);
+  }
   RowsPartEntry& e = cache[cache_next];
   cache_next = (cache_next + 1) % 8;
-  e.key = key; memcpy(e.bound, S.bound, sizeof(S.bound)); e.valid = true;
+  e.key = key; memcpy(e.bound, S.bound, sizeof(S.bound)); e.cut = S.cut; e.valid = true;
 }
 
 template <bool EXACT, int INTERP>
 static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const BwdWs& L, char* ws, bool forced) {
-  constexpr int NT = Stencil<INTERP>::NT;
+  constexpr int NT = Stencil<INTERP>::NT, OMIN = Stencil<INTERP>::OMIN;
   const int H = P.H, W = P.W, planes = P.B * P.V;
   if (!(cfl_cells > 0.0f) || H < 8 || W < 32 || W > 32767) return false;
   const int rr = (int)ceil((double)cfl_cells);
@@ -1052,11 +1089,25 @@ static bool launch_rows(const Params& P, cudaStream_t st, float cfl_cells, const
   if (grid < 1) grid = 1;
   if (grid > nsm) grid = nsm;
   if (grid > kRowsMaxCtas) grid = kRowsMaxCtas;
+  // Cut mode (see RowsPlan::cut): on for latitude bands, where a CTA owns few rows and the ring - 1 warm-up rows of
+  // every segment weigh most (8-way split of C3: band backward 0.32 / 0.30 -> 0.275 ms); a full mesh gains nothing
+  // (1.58 ms either way).  PARADIS_SL_ROWS_CUT = 0 / 1 forces it off / on.
+  static const int env_cut = env_int("PARADIS_SL_ROWS_CUT", -1);
+  const bool want_cut = env_cut < 0 ? P.ownN < H : env_cut != 0;
+  S.GR = rr + NT;
+  S.grow = (float*)(ws + L.grow);
+  S.cut = (want_cut && S.GR <= kRowsMaxGuardRows &&
+           (size_t)grid * 2 * S.GR * nS * S.pitch * sizeof(float) <= L.grow_bytes) ? 1 : 0;
   rows_partition<INTERP>(P, S, reach, wc, planes, grid);
   kern<<<grid, kRowsWarps * 32, smem, st>>>(P, S);
   {
     const long long nfix = (long long)S.total_rows * nS * (NT - 1);
     rows_guard_fix_kernel<<<(unsigned)((nfix + 255) / 256), 256, 0, st>>>(P.gfield, S.guard, S.total_rows, W, nS, wc, NT - 1);
+  }
+  if (S.cut) {
+    const dim3 fgrid((W / 4 + 127) / 128, S.GR, grid);
+    for (int side = 1; side >= 0; --side)
+      rows_grow_fix_kernel<<<fgrid, 128, 0, st>>>(P.gfield, S, side, W, P.own0, P.ownN, NT, OMIN);
   }
   if (P.pole_fix) {
     // adjoint of the first enforce_pole_continuity (advection.py:129): pole rows of grad_field get their zonal mean

@@ -73,6 +73,11 @@ struct RowsPlan {
   int wc;                          // strip width (multiple of 4)
   int pitch, ring_stride;          // private ring of a consumer: (ring + NT - 1) rows of `pitch` floats = ring_stride
   float* guard;                    // [planes][outN][nS][NT - 1] guard columns of the retired rows (added by a post-kernel)
+  int cut;                         // 1: a CTA range that starts / ends inside a plane does not replay the ring warm-up rows
+                                   // of its neighbour; the partial destination rows either side of the cut go to `grow`
+  int GR;                          // guard rows kept per side of a cut (rr + NT)
+  float* grow;                     // [CTAs][2][GR][nS][pitch] partial destination rows beyond a cut (0: below the
+                                   // start of the CTA's first segment, 1: above the end of its last one)
   int nsteps;                      // producer steps per arrival row = ceil(W / 128)
   int total_rows;                  // planes * ownN
   int bound[kRowsMaxCtas + 1];     // CTA k owns rows [bound[k], bound[k + 1]) of the concatenated (plane, own row)
@@ -115,7 +120,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-struct RowsSeg { int pl, ra, rb, y_first, y_last; };   // destination rows [ra, rb) of plane pl (global rows)
+// destination rows [ra, rb) of plane pl (global rows); arrival rows y_first .. y_last are processed (cut mode: a
+// segment that starts / ends inside its plane processes its own arrival rows only, and its consumers flush the
+// ring - 1 rows still in the ring after the last one)
+struct RowsSeg { int pl, ra, rb, y_first, y_last; };
 
 template <int INTERP>
 __device__ __forceinline__ bool rows_next_seg(const Params& P, const RowsPlan& S, int& g, int g1, RowsSeg& s) {
@@ -126,8 +134,8 @@ __device__ __forceinline__ bool rows_next_seg(const Params& P, const RowsPlan& S
   const int n = min(P.ownN - r, g1 - g);
   s.ra = P.own0 + r; s.rb = s.ra + n;
   // destination row i = y - rr + OMIN is complete after arrival row y
-  s.y_first = s.ra - (S.ring - 1) + S.rr - OMIN;
-  s.y_last = s.rb - 1 + S.rr - OMIN;
+  s.y_first = (S.cut && r > 0) ? s.ra : s.ra - (S.ring - 1) + S.rr - OMIN;       // starts / ends at a cut inside the plane
+  s.y_last = (S.cut && r + n < P.ownN) ? s.rb - 1 : s.rb - 1 + S.rr - OMIN;
   g += n;
   return true;
 }
@@ -378,6 +386,41 @@ __device__ __forceinline__ void rows_pair(const Params& P, const float* __restri
     else rec[e] = make_float4(tx, ty, ge, __int_as_float(key));
   }
   if (core) velocity_grads_2(P, t2, f2s(sp), f2s(cp), mul2(g, make_float2(ddx[0], ddx[1])), mul2(g, make_float2(ddy[0], ddy[1])), ou, ov);
+}
+
+// ---- cold paths of the cut mode (not inlined: the hot loops of the kernel keep their register allocation) ----
+__device__ __noinline__ void rows_park_row(const float* row, float* dst, int pitch, int lane) {
+  for (int k = 4 * lane; k < pitch; k += 128)
+    __stcs(reinterpret_cast<float4*>(dst + k), *reinterpret_cast<const float4*>(row + k));
+}
+
+// retire ring slot `head` without a new arrival row: alias rows in, row out (own row -> orow + guard columns gcol;
+// partial row beyond the cut -> park; neither -> dropped), slot cleared
+__device__ __noinline__ void rows_flush_row(float* ringp, int head, int ring, int pitch, int wc, int ng, float* orow,
+                                            float* gcol, float* park, int lane) {
+  float* row = ringp + head * pitch;
+  if (head < ng) {
+    float* alias = ringp + (ring + head) * pitch;
+    for (int k = 4 * lane; k < pitch; k += 128) {
+      float4 a = *reinterpret_cast<const float4*>(row + k);
+      const float4 b = *reinterpret_cast<const float4*>(alias + k);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      *reinterpret_cast<float4*>(row + k) = a;
+      *reinterpret_cast<float4*>(alias + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+  }
+  if (orow) {
+    for (int k = 4 * lane; k < wc; k += 128)
+      __stcs(reinterpret_cast<float4*>(orow + k), *reinterpret_cast<const float4*>(row + k));
+    if (lane < ng) gcol[lane] = row[wc + lane];
+  } else if (park) {
+    for (int k = 4 * lane; k < pitch; k += 128)
+      __stcs(reinterpret_cast<float4*>(park + k), *reinterpret_cast<const float4*>(row + k));
+  }
+  __syncwarp();
+  for (int k = 4 * lane; k < pitch; k += 128) *reinterpret_cast<float4*>(row + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
 }
 
 template <bool EXACT, int INTERP, bool PEER>
@@ -659,12 +702,39 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 1) sl_bwd_rows_kernel(const P
               __stcs(reinterpret_cast<float4*>(orow + k), *reinterpret_cast<const float4*>(row + k));
             if (lane < NT - 1)
               guard_pl[((long long)(i - S.out0) * S.nS + sidx[q]) * (NT - 1) + lane] = row[T[q].wc + lane];
+          } else if (S.cut && i < sg.ra && i >= P.own0 && sg.ra > P.own0) {
+            // cut mode, rows below the start cut: partial rows of the neighbouring segment (this segment's arrival rows
+            // reach across the cut); the whole ring row, guard columns included, is parked for rows_grow_fix_kernel
+            rows_park_row(row, S.grow + ((((size_t)blockIdx.x * 2) * S.GR + (i - (sg.ra - S.GR))) * S.nS + sidx[q]) * pitch,
+                          pitch, lane);
           }
           __syncwarp();
           for (int k = 4 * lane; k < pitch; k += 128) *reinterpret_cast<float4*>(row + k) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();
         head = head + 1 == ring ? 0 : head + 1;
+      }
+      if (S.cut && sg.rb < P.own0 + P.ownN) {
+        // cut mode, end cut: retire the ring - 1 rows still in the ring -- the last own rows, then the partial rows
+        // above the cut (parked; rows outside the own window belong to a latitude neighbour or do not exist)
+        for (int t = 0; t < ring - 1; ++t) {
+          const int i = sg.y_last + 1 + t - rr + OMIN;
+#pragma unroll
+          for (int q = 0; q < kStreams; ++q) {
+            if (T[q].wc <= 0) continue;
+            // (a segment shorter than the ring still holds rows BELOW its start cut here)
+            const bool own = i >= sg.ra && i < sg.rb;
+            float* orow = own ? gf_pl + (long long)(i - S.out0) * W + T[q].ja : nullptr;
+            float* gcol = own ? guard_pl + ((long long)(i - S.out0) * S.nS + sidx[q]) * (NT - 1) : nullptr;
+            float* park = nullptr;
+            if (i >= sg.rb && i < P.own0 + P.ownN)
+              park = S.grow + ((((size_t)blockIdx.x * 2 + 1) * S.GR + (i - sg.rb)) * S.nS + sidx[q]) * pitch;
+            else if (i < sg.ra && i >= P.own0 && sg.ra > P.own0)
+              park = S.grow + ((((size_t)blockIdx.x * 2) * S.GR + (i - (sg.ra - S.GR))) * S.nS + sidx[q]) * pitch;
+            rows_flush_row(T[q].ring, head, ring, pitch, T[q].wc, NT - 1, orow, gcol, park, lane);
+          }
+          head = head + 1 == ring ? 0 : head + 1;
+        }
       }
     }
   }
@@ -682,6 +752,38 @@ __global__ void rows_guard_fix_kernel(float* __restrict__ gfield, const float* _
   int col = min((c + 1) * wc, W) + gcol;
   if (col >= W) col -= W;
   gfield[row * W + col] += guard[idx];
+}
+
+// Cut mode: the partial destination rows a CTA accumulated beyond the cuts of its range are added to the rows their
+// owner stored.  One launch per side (first the rows above the ends, then the rows below the starts); cuts of one plane
+// are at least GR rows apart (host partition), so within a launch every gfield element has at most one source.  A guard
+// row is a whole ring row per strip: `wc` main columns plus NT - 1 guard columns that belong to the next strip's first
+// columns (the last strip's wrap to column 0), as in rows_guard_fix_kernel.
+__global__ void rows_grow_fix_kernel(float* __restrict__ gfield, const RowsPlan S, int side, int W, int own0, int ownN,
+                                     int NT, int OMIN) {
+  // grid: x = float4 groups of a row, y = guard row j, z = CTA of the sweep
+  const int c = blockIdx.z, j = blockIdx.y;
+  const int col = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (col >= W || S.bound[c + 1] <= S.bound[c]) return;
+  const int g = side ? S.bound[c + 1] : S.bound[c];
+  const int pl = g / ownN, r = g - pl * ownN;
+  if (r == 0) return;                                        // a plane boundary (or the end of the work) is not a cut
+  const int il = side ? r + j : r - S.GR + j;                // own-row index of the destination row
+  if (side) { if (j >= S.rr + OMIN + NT - 1 || il >= ownN) return; }
+  else      { if (j < S.GR - (S.rr - OMIN) || il < 0) return; }
+  const int s = col / S.wc, k = col - s * S.wc;              // strips start at multiples of 4: one strip per float4
+  const float* blk = S.grow + (((size_t)c * 2 + side) * S.GR + j) * S.nS * S.pitch;
+  float4 v = *reinterpret_cast<const float4*>(blk + s * S.pitch + k);
+  if (k == 0) {
+    const int sp = s == 0 ? S.nS - 1 : s - 1;
+    const float* gc = blk + sp * S.pitch + (min((sp + 1) * S.wc, W) - sp * S.wc);
+    v.x += gc[0];
+    if (NT - 1 > 1) { v.y += gc[1]; v.z += gc[2]; }
+  }
+  float4* dst = reinterpret_cast<float4*>(gfield + ((long long)pl * S.outN + (own0 + il - S.out0)) * W + col);
+  float4 a = *dst;
+  a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  *dst = a;
 }
 
 }  // namespace psl

@@ -38,7 +38,8 @@ def relmax(a, b):
 def check():
     cases = [(33, 64, 2, 2, True, 2.0, 3.0), (64, 128, 1, 4, True, 2.0, 6.0), (128, 256, 2, 3, False, 4.0, 6.0),
              (181, 360, 1, 3, True, 4.0, 6.0), (181, 360, 1, 3, True, 1.0, 8.0), (96, 192, 2, 3, True, 8.0, 8.0),
-             (721, 1440, 1, 2, True, 4.0, 6.0), (240, 512, 1, 2, False, 1.5, 2.0)]
+             (721, 1440, 1, 2, True, 4.0, 6.0), (240, 512, 1, 2, False, 1.5, 2.0),
+             (181, 360, 2, 32, True, 4.0, 6.0), (721, 1440, 1, 8, True, 4.0, 6.0)]   # many planes: every CTA range cut
     ok = True
     for interp in ("bilinear", "bicubic"):
         for (H, W, B, V, poles, clip, cfl) in cases:
