@@ -21,14 +21,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, H, W, cfl, interp, q):
+def _worker(rank, world, port, H, W, cfl, interp, q, balance=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         g = torch.Generator().manual_seed(0)
         full = torch.randn(2, 3, H, W, generator=g)
-        plan = halo.make_plan(H, W, rank, world, cfl, interp)
+        plan = halo.make_plan(H, W, rank, world, cfl, interp, balance=balance)
         own = full[:, :, plan.row0:plan.row0 + plan.rows].contiguous()
         ext = halo.exchange_rows(own, plan)
         ok = torch.equal(ext, full[:, :, plan.ext_row0:plan.ext_row0 + plan.ext_rows])
@@ -38,17 +38,18 @@ def _worker(rank, world, port, H, W, cfl, interp, q):
         ok = ok and torch.equal(a, ref) and torch.equal(b, ref * 2) and torch.equal(c, ref * 3)
         (own_w, ext_w) = plan.windows()
         ok = ok and own_w == (plan.row0, plan.rows) and ext_w[0] >= 0 and ext_w[0] + ext_w[1] <= H
-        q.put((rank, bool(ok), plan.lo, plan.hi))
+        q.put((rank, bool(ok), plan.lo, plan.hi, plan.rows))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,H", [(2, 64), (3, 91)])
-def test_exchange_rows_gloo(world, H):
+@pytest.mark.parametrize("world,H,W,balance", [(2, 64, 32, False), (3, 91, 32, False), (3, 181, 360, True)])
+def test_exchange_rows_gloo(world, H, W, balance):
+    """balance=True: bands of unequal height from the cost-levelled split (polar bands thinner)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, H, 32, 3.0, "bilinear", q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, H, W, 3.0, "bilinear", q, balance)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in range(world))
@@ -58,6 +59,9 @@ def test_exchange_rows_gloo(world, H):
     assert all(r[1] for r in res)
     assert res[0][2] == 0 and res[-1][3] == 0           # no halo beyond the poles
     assert all(r[3] == halo.halo_rows(3.0, "bilinear") for r in res[:-1])
+    assert sum(r[4] for r in res) == H
+    if balance:
+        assert res[0][4] < res[1][4] and res[-1][4] < res[1][4]
 
 
 def test_band_rows_and_plan():
