@@ -27,6 +27,11 @@
 // hit the same departure cell are detected with one-byte tags and summed into the lowest lane in lane
 // order (resolve_clashes), so every add has a single writer and a data-defined order.
 //
+// Cut mode (RowsPlan::cut, latitude bands): a segment that starts / ends inside a plane processes only its own
+// arrival rows instead of replaying ring - 1 rows of its neighbour; the destination rows its arrival rows reach
+// beyond the cut are parked (rows_park_row / rows_flush_row) and added to the rows their owner stored by
+// rows_grow_fix_kernel -- one source per element and launch, so the result stays bit-reproducible.
+//
 // Pipelines (all mbarrier based, no __syncthreads after start-up):
 //   stage_full / stage_free [kRowStages]   loader -> producers   (TMA transaction count / nP arrivals)
 //   rec_full   / rec_free   [kRowRecs]     producers -> consumers (nP arrivals / nC arrivals)
